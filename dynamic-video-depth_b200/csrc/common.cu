@@ -1,0 +1,31 @@
+// Error reporting + device queries shared by every translation unit of libdvd_b200.so.
+#include "common.cuh"
+#include <string.h>
+
+namespace dvd {
+
+static thread_local char g_err[512] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+    cached = n;
+    return n;
+  }
+  return 148;  // B200
+}
+
+}  // namespace dvd
+
+extern "C" const char* dvd_last_error(void) { return dvd::g_err; }
+extern "C" int dvd_version(void) { return 100; }

@@ -1,0 +1,648 @@
+// Fused un-project -> scene-flow-advect -> re-project -> bilinear flow-warp -> consistency-loss chain.
+//
+// Replaces (reference paths relative to the reference tree):
+//   unproject_ptcld.forward                 losses/scene_flow_projection.py:48-67      (W3)
+//   flow_by_depth.forward                   losses/scene_flow_projection.py:95-153     (W1)
+//   scene_flow_projection_slack.forward     losses/scene_flow_projection.py:204-278    (W2)
+//   backward_warp + ATen grid_sampler_2d    losses/scene_flow_projection.py:103-112    (bilinear, border, align_corners=True)
+//   Model._calc_loss / Model.disp_loss      models/scene_flow_motion_field.py:285-324,140-150 (L1)
+//
+// The reference runs ~100 ATen launches (16 broadcast 1x3·3x3 batched GEMMs, 3 grid_samples, 3
+// nonzero+index_put pairs with host syncs) and materialises ~27 floats/pixel. Here the whole chain is
+// one elementwise + gather kernel per direction: it is HBM-bound (no contraction => no tensor cores),
+// so the design goals are coalesced 64/128-bit streaming loads, zero intermediate tensors, per-block
+// partial sums through warp shuffles, and atomics only for the bilinear scatter of d(depth_2).
+//
+// Algorithmic HBM bytes per pixel (fp32): fwd 32 (d1 4, d2 4, flow 8, mask 4, sf 12);
+// bwd 48 (the same 32 read + g_sf 12 + g_d2 4 written). See DESIGN.md for the full accounting.
+#include "common.cuh"
+#include <initializer_list>
+
+namespace dvd {
+
+struct Pose {
+  float Kinv[9], K[9], R1[9], R2[9], t1[3], t2[3];
+};
+static_assert(sizeof(Pose) == 42 * sizeof(float), "pose layout");
+
+__device__ __forceinline__ void load_pose(Pose& dst, const float* __restrict__ poses, int b) {
+  // cooperative copy of one pair's pose block into shared memory
+  float* d = reinterpret_cast<float*>(&dst);
+  for (int i = threadIdx.x; i < 42; i += blockDim.x) d[i] = __ldg(poses + (size_t)b * DVD_POSE_STRIDE + i);
+}
+
+__device__ __forceinline__ void mv(const float* M, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = fmaf(M[2], z, fmaf(M[1], y, M[0] * x));
+  oy = fmaf(M[5], z, fmaf(M[4], y, M[3] * x));
+  oz = fmaf(M[8], z, fmaf(M[7], y, M[6] * x));
+}
+__device__ __forceinline__ void mtv(const float* M, float x, float y, float z, float& ox, float& oy, float& oz) {
+  ox = fmaf(M[6], z, fmaf(M[3], y, M[0] * x));
+  oy = fmaf(M[7], z, fmaf(M[4], y, M[1] * x));
+  oz = fmaf(M[8], z, fmaf(M[5], y, M[2] * x));
+}
+// ray = Kinv * (x, y, 1)
+__device__ __forceinline__ void ray_of(const float* Kinv, float x, float y, float& rx, float& ry, float& rz) {
+  rx = fmaf(Kinv[1], y, Kinv[0] * x) + Kinv[2];
+  ry = fmaf(Kinv[4], y, Kinv[3] * x) + Kinv[5];
+  rz = fmaf(Kinv[7], y, Kinv[6] * x) + Kinv[8];
+}
+
+// Bilinear taps of ATen grid_sampler_2d(bilinear, padding_mode=border, align_corners=True) for the pixel
+// coordinate (qx,qy). The reference normalises to [-1,1] (losses/...:107-110) and ATen un-normalises;
+// the round trip is reproduced so fp32 rounding follows the reference.
+struct Taps {
+  int idx[4];    // linear index y*W+x of nw, ne, sw, se (clamped in range)
+  float w[4];    // weights, 0 for out-of-range taps
+  float ux[2], uy[2];  // tap coordinates as floats: x0,x1 / y0,y1
+};
+__device__ __forceinline__ Taps make_taps(float qx, float qy, int H, int W) {
+  const float hw = (float)(W - 1), hh = (float)(H - 1);
+  float gx = qx / (hw * 0.5f) - 1.0f;
+  float gy = qy / (hh * 0.5f) - 1.0f;
+  float ix = ((gx + 1.0f) / 2.0f) * hw;
+  float iy = ((gy + 1.0f) / 2.0f) * hh;
+  ix = fminf(hw, fmaxf(ix, 0.0f));
+  iy = fminf(hh, fmaxf(iy, 0.0f));
+  float x0f = floorf(ix), y0f = floorf(iy);
+  float wx1 = ix - x0f, wy1 = iy - y0f;
+  float wx0 = (x0f + 1.0f) - ix, wy0 = (y0f + 1.0f) - iy;
+  int x0 = (int)x0f, y0 = (int)y0f;
+  int x1 = x0 + 1, y1 = y0 + 1;
+  bool vx1 = x1 <= W - 1, vy1 = y1 <= H - 1;
+  int x1c = vx1 ? x1 : x0, y1c = vy1 ? y1 : y0;
+  Taps t;
+  t.idx[0] = y0 * W + x0;
+  t.idx[1] = y0 * W + x1c;
+  t.idx[2] = y1c * W + x0;
+  t.idx[3] = y1c * W + x1c;
+  t.w[0] = wx0 * wy0;
+  t.w[1] = vx1 ? wx1 * wy0 : 0.0f;
+  t.w[2] = vy1 ? wx0 * wy1 : 0.0f;
+  t.w[3] = (vx1 && vy1) ? wx1 * wy1 : 0.0f;
+  t.ux[0] = x0f; t.ux[1] = (float)x1c;
+  t.uy[0] = y0f; t.uy[1] = (float)y1c;
+  return t;
+}
+
+// Everything the forward chain produces for one pixel.
+struct Px {
+  float P1[3];      // global_p1
+  float wpc[3];     // warped_p2_camera_2
+  float wP2[3];     // warped_global_p2
+  float wd;         // depth_warp_1_2
+  float p12[3];     // p1_camera_2
+  float i12[3];     // K * p12 (z = depth_image_1_2)
+  float dflow[2];   // dflow_1_2
+  bool zok;         // i12.z >= 1e-3 (projection used; otherwise own coordinate, zero gradient)
+};
+
+template <bool kNeedWorld>
+__device__ __forceinline__ void forward_px(const Pose& ps, const float* __restrict__ d2img, const Taps& tp,
+                                           float x, float y, float d1, float sfx, float sfy, float sfz, Px& o) {
+  float rx, ry, rz;
+  ray_of(ps.Kinv, x, y, rx, ry, rz);
+  float cx = d1 * rx, cy = d1 * ry, cz = d1 * rz;
+  mv(ps.R1, cx, cy, cz, o.P1[0], o.P1[1], o.P1[2]);
+  o.P1[0] += ps.t1[0]; o.P1[1] += ps.t1[1]; o.P1[2] += ps.t1[2];
+  // bilinear gather of depth_2-derived quantities (4 taps, order nw, ne, sw, se like ATen)
+  o.wpc[0] = o.wpc[1] = o.wpc[2] = 0.0f;
+  o.wP2[0] = o.wP2[1] = o.wP2[2] = 0.0f;
+  o.wd = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float dv = __ldg(d2img + tp.idx[k]);
+    float tx, ty, tz;
+    ray_of(ps.Kinv, tp.ux[k & 1], tp.uy[k >> 1], tx, ty, tz);
+    float px = dv * tx, py = dv * ty, pz = dv * tz;
+    float w = tp.w[k];
+    o.wpc[0] = fmaf(w, px, o.wpc[0]);
+    o.wpc[1] = fmaf(w, py, o.wpc[1]);
+    o.wpc[2] = fmaf(w, pz, o.wpc[2]);
+    o.wd = fmaf(w, dv, o.wd);
+    if (kNeedWorld) {
+      float gx, gy, gz;
+      mv(ps.R2, px, py, pz, gx, gy, gz);
+      o.wP2[0] = fmaf(w, gx + ps.t2[0], o.wP2[0]);
+      o.wP2[1] = fmaf(w, gy + ps.t2[1], o.wP2[1]);
+      o.wP2[2] = fmaf(w, gz + ps.t2[2], o.wP2[2]);
+    }
+  }
+  // p12 = R2^T (P1 + sf - t2);  i12 = K p12
+  float vx = o.P1[0] + sfx - ps.t2[0], vy = o.P1[1] + sfy - ps.t2[1], vz = o.P1[2] + sfz - ps.t2[2];
+  mtv(ps.R2, vx, vy, vz, o.p12[0], o.p12[1], o.p12[2]);
+  mv(ps.K, o.p12[0], o.p12[1], o.p12[2], o.i12[0], o.i12[1], o.i12[2]);
+  o.zok = !(o.i12[2] < 1e-3f);
+  if (o.zok) {
+    float zi = o.i12[2] + 1e-8f;
+    o.dflow[0] = o.i12[0] / zi - x;
+    o.dflow[1] = o.i12[1] / zi - y;
+  } else {
+    o.dflow[0] = 0.0f;
+    o.dflow[1] = 0.0f;
+  }
+}
+
+__device__ __forceinline__ float mask_of(const dvd_loss_cfg& c, float m2, float d1, float wz) {
+  float m = m2;
+  if (c.midas) {
+    m *= (d1 < 100.0f) ? 1.0f : 0.0f;
+    m *= (wz < 100.0f) ? 1.0f : 0.0f;
+  }
+  return m;
+}
+
+__device__ __forceinline__ float disp_term(const dvd_loss_cfg& c, float za, float zb) {
+  if (c.disp_mode == 0) {
+    float a = fmaxf(za, 1e-3f), b = fmaxf(zb, 1e-3f);
+    return 100.0f * fabsf(1.0f / a - 1.0f / b);
+  } else if (c.disp_mode == 1) {
+    float a = fmaxf(za, 1e-3f), b = fmaxf(zb, 1e-3f);
+    return fmaxf(a, b) / fminf(a, b) - 1.0f;
+  }
+  return fabsf(za - zb);
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector access helpers: VEC consecutive pixels along x per thread
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using T = float;  using F = float2; };
+template <> struct VecT<2> { using T = float2; using F = float4; };
+template <> struct VecT<4> { using T = float4; using F = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[VEC]) {
+  if (VEC == 4) {
+    float4 t = ldg_stream4(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if (VEC == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&v)[VEC]) {
+  if (VEC == 4) {
+    st_stream4(p, make_float4(v[0], v[1], v[2], v[3]));
+  } else if (VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  } else {
+    *p = v[0];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void load_flow(const float* __restrict__ p, float (&fx)[VEC], float (&fy)[VEC]) {
+  // p points at flow[b,y,x,0]; 2*VEC consecutive floats
+  if (VEC == 4) {
+    float4 a = ldg_stream4(p), b = ldg_stream4(p + 4);
+    fx[0] = a.x; fy[0] = a.y; fx[1] = a.z; fy[1] = a.w;
+    fx[2] = b.x; fy[2] = b.y; fx[3] = b.z; fy[3] = b.w;
+  } else if (VEC == 2) {
+    float4 a = ldg_stream4(p);
+    fx[0] = a.x; fy[0] = a.y; fx[1] = a.z; fy[1] = a.w;
+  } else {
+    float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    fx[0] = a.x; fy[0] = a.y;
+  }
+}
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// un-project forward / adjoint
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) unproject_fwd_kernel(const float* __restrict__ depth,
+                                                                 const float* __restrict__ poses,
+                                                                 float* __restrict__ P, int H, int W, int which) {
+  __shared__ Pose ps;
+  const int b = blockIdx.y;
+  load_pose(ps, poses, b);
+  __syncthreads();
+  const float* R = which == 1 ? ps.R1 : ps.R2;
+  const float* t = which == 1 ? ps.t1 : ps.t2;
+  const int HW = H * W, items = HW / VEC, Wv = W / VEC;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    int y = it / Wv, x0 = (it - y * Wv) * VEC;
+    size_t pix = (size_t)y * W + x0;
+    float d[VEC], ox[VEC], oy[VEC], oz[VEC];
+    load_vec<VEC>(depth + (size_t)b * HW + pix, d);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float rx, ry, rz;
+      ray_of(ps.Kinv, (float)(x0 + v), (float)y, rx, ry, rz);
+      mv(R, d[v] * rx, d[v] * ry, d[v] * rz, ox[v], oy[v], oz[v]);
+      ox[v] += t[0]; oy[v] += t[1]; oz[v] += t[2];
+    }
+    float* o = P + (size_t)b * 3 * HW + pix;
+    store_vec<VEC>(o, ox);
+    store_vec<VEC>(o + HW, oy);
+    store_vec<VEC>(o + 2 * (size_t)HW, oz);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) unproject_bwd_kernel(const float* __restrict__ gP,
+                                                                 const float* __restrict__ poses,
+                                                                 float* __restrict__ gd, int H, int W, int which) {
+  __shared__ Pose ps;
+  const int b = blockIdx.y;
+  load_pose(ps, poses, b);
+  __syncthreads();
+  const float* R = which == 1 ? ps.R1 : ps.R2;
+  const int HW = H * W, items = HW / VEC, Wv = W / VEC;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    int y = it / Wv, x0 = (it - y * Wv) * VEC;
+    size_t pix = (size_t)y * W + x0;
+    float gx[VEC], gy[VEC], gz[VEC], o[VEC];
+    const float* g = gP + (size_t)b * 3 * HW + pix;
+    load_vec<VEC>(g, gx);
+    load_vec<VEC>(g + HW, gy);
+    load_vec<VEC>(g + 2 * (size_t)HW, gz);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float rx, ry, rz, wx, wy, wz;
+      ray_of(ps.Kinv, (float)(x0 + v), (float)y, rx, ry, rz);
+      mv(R, rx, ry, rz, wx, wy, wz);  // dP/dd = R * ray
+      o[v] = fmaf(gz[v], wz, fmaf(gy[v], wy, gx[v] * wx));
+    }
+    store_vec<VEC>(gd + (size_t)b * HW + pix, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused forward: loss partial sums only
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) reproject_loss_fwd_kernel(
+    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
+    const float* __restrict__ mask_2, const float* __restrict__ sf, const float* __restrict__ poses,
+    dvd_loss_cfg cfg, float* __restrict__ partials, int H, int W) {
+  __shared__ Pose ps;
+  __shared__ float red[kThreads / 32][4];
+  const int b = blockIdx.y;
+  load_pose(ps, poses, b);
+  __syncthreads();
+  const int HW = H * W, items = HW / VEC, Wv = W / VEC;
+  const float* d2img = depth_2 + (size_t)b * HW;
+  float s_flow = 0.f, s_disp = 0.f, s_sf = 0.f, s_m = 0.f;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    int y = it / Wv, x0 = (it - y * Wv) * VEC;
+    size_t pix = (size_t)y * W + x0;
+    float d1[VEC], m2[VEC], sx[VEC], sy[VEC], sz[VEC], fx[VEC], fy[VEC];
+    load_vec<VEC>(depth_1 + (size_t)b * HW + pix, d1);
+    load_vec<VEC>(mask_2 + (size_t)b * HW + pix, m2);
+    const float* sfp = sf + (size_t)b * 3 * HW + pix;
+    load_vec<VEC>(sfp, sx);
+    load_vec<VEC>(sfp + HW, sy);
+    load_vec<VEC>(sfp + 2 * (size_t)HW, sz);
+    load_flow<VEC>(flow + ((size_t)b * HW + pix) * 2, fx, fy);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float x = (float)(x0 + v), yf = (float)y;
+      Taps tp = make_taps(x + fx[v], yf + fy[v], H, W);
+      Px o;
+      forward_px<true>(ps, d2img, tp, x, yf, d1[v], sx[v], sy[v], sz[v], o);
+      float m = mask_of(cfg, m2[v], d1[v], o.wpc[2]);
+      float ex = o.dflow[0] - fx[v], ey = o.dflow[1] - fy[v];
+      float fl = cfg.warm ? (ex * ex + ey * ey) : (fabsf(ex) + fabsf(ey));
+      float dl = disp_term(cfg, o.p12[2], o.wpc[2]);
+      float sl = fabsf(o.wP2[0] - o.P1[0] - sx[v]) + fabsf(o.wP2[1] - o.P1[1] - sy[v]) +
+                 fabsf(o.wP2[2] - o.P1[2] - sz[v]);
+      s_flow = fmaf(m, fl, s_flow);
+      s_disp = fmaf(m, dl, s_disp);
+      s_sf = fmaf(m, sl, s_sf);
+      s_m += m;
+    }
+  }
+  s_flow = warp_sum(s_flow); s_disp = warp_sum(s_disp); s_sf = warp_sum(s_sf); s_m = warp_sum(s_m);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[wid][0] = s_flow; red[wid][1] = s_disp; red[wid][2] = s_sf; red[wid][3] = s_m; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) a += red[w][threadIdx.x];
+    partials[((size_t)b * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = a;
+  }
+}
+
+// deterministic final reduction (fixed order, double accumulation) + loss assembly
+__global__ void __launch_bounds__(256) reproject_finalize_kernel(const float* __restrict__ partials, int n_quads,
+                                                                 dvd_loss_cfg cfg, float* __restrict__ scalars) {
+  __shared__ double red[8][4];
+  double acc[4] = {0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n_quads; i += blockDim.x) {
+    float4 q = *reinterpret_cast<const float4*>(partials + (size_t)i * 4);
+    acc[0] += q.x; acc[1] += q.y; acc[2] += q.z; acc[3] += q.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) for (int k = 0; k < 4; ++k) red[wid][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[4] = {0, 0, 0, 0};
+    for (int w = 0; w < 8; ++w) for (int k = 0; k < 4; ++k) t[k] += red[w][k];
+    float n = (float)t[3] + 1e-8f;  // torch.sum(occ_mask) + 1e-8 (smf.py:297-306)
+    float fl = (float)t[0] / n, dl = (float)t[1] / n, sl = (float)t[2] / n;
+    float second = cfg.second_is_disp ? dl : sl;
+    scalars[DVD_S_FLOW] = fl;
+    scalars[DVD_S_DISP] = dl;
+    scalars[DVD_S_SF] = sl;
+    scalars[DVD_S_LOSS] = cfg.flow_mul * fl + cfg.disp_mul * second;
+    scalars[DVD_S_MASKSUM] = (float)t[3];
+    scalars[DVD_S_CF] = cfg.flow_mul / n;
+    scalars[DVD_S_CD] = cfg.disp_mul / n;
+    scalars[DVD_S_RSVD] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused backward: g_sf (== g_global_p1) and scatter-add of g_depth_2
+__device__ __forceinline__ float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) reproject_loss_bwd_kernel(
+    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
+    const float* __restrict__ mask_2, const float* __restrict__ sf, const float* __restrict__ poses,
+    dvd_loss_cfg cfg, const float* __restrict__ scalars, float gscale, const float* __restrict__ gscale_dev,
+    float* __restrict__ g_sf,
+    float* __restrict__ g_d2, int H, int W) {
+  __shared__ Pose ps;
+  const int b = blockIdx.y;
+  load_pose(ps, poses, b);
+  __syncthreads();
+  const float gs = gscale * (gscale_dev ? __ldg(gscale_dev) : 1.0f);
+  const float cf = __ldg(scalars + DVD_S_CF) * gs;
+  const float cd = __ldg(scalars + DVD_S_CD) * gs;
+  const int HW = H * W, items = HW / VEC, Wv = W / VEC;
+  const float* d2img = depth_2 + (size_t)b * HW;
+  float* gd2img = g_d2 ? g_d2 + (size_t)b * HW : nullptr;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    int y = it / Wv, x0 = (it - y * Wv) * VEC;
+    size_t pix = (size_t)y * W + x0;
+    float d1[VEC], m2[VEC], sx[VEC], sy[VEC], sz[VEC], fx[VEC], fy[VEC];
+    float ox[VEC], oy[VEC], oz[VEC];
+    load_vec<VEC>(depth_1 + (size_t)b * HW + pix, d1);
+    load_vec<VEC>(mask_2 + (size_t)b * HW + pix, m2);
+    const float* sfp = sf + (size_t)b * 3 * HW + pix;
+    load_vec<VEC>(sfp, sx);
+    load_vec<VEC>(sfp + HW, sy);
+    load_vec<VEC>(sfp + 2 * (size_t)HW, sz);
+    load_flow<VEC>(flow + ((size_t)b * HW + pix) * 2, fx, fy);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float x = (float)(x0 + v), yf = (float)y;
+      Taps tp = make_taps(x + fx[v], yf + fy[v], H, W);
+      Px o;
+      if (cfg.second_is_disp) forward_px<false>(ps, d2img, tp, x, yf, d1[v], sx[v], sy[v], sz[v], o);
+      else                    forward_px<true>(ps, d2img, tp, x, yf, d1[v], sx[v], sy[v], sz[v], o);
+      float m = mask_of(cfg, m2[v], d1[v], o.wpc[2]);
+      // --- gradient w.r.t. i12 = K p12 from the flow term
+      float gi0 = 0.f, gi1 = 0.f, gi2 = 0.f;
+      if (o.zok) {
+        float ex = o.dflow[0] - fx[v], ey = o.dflow[1] - fy[v];
+        float gux = cfg.warm ? 2.f * ex : sgn(ex);
+        float guy = cfg.warm ? 2.f * ey : sgn(ey);
+        gux *= m * cf; guy *= m * cf;
+        float zi = o.i12[2] + 1e-8f, rz = 1.0f / zi;
+        gi0 = gux * rz;
+        gi1 = guy * rz;
+        gi2 = -(gux * o.i12[0] + guy * o.i12[1]) * rz * rz;
+      }
+      float gp0, gp1, gp2;  // g_p12 = K^T g_i12
+      mtv(ps.K, gi0, gi1, gi2, gp0, gp1, gp2);
+      float gwc0 = 0.f, gwc1 = 0.f, gwc2 = 0.f;  // g_warped_p2_camera_2
+      float ge0 = 0.f, ge1 = 0.f, ge2 = 0.f;     // g_(sf_by_depth - sf)
+      if (cfg.second_is_disp) {
+        float za = o.p12[2], zb = o.wpc[2];
+        float mc = m * cd;
+        if (cfg.disp_mode == 0) {
+          float a = fmaxf(za, 1e-3f), bb = fmaxf(zb, 1e-3f);
+          float s = 100.f * sgn(1.0f / a - 1.0f / bb) * mc;
+          if (za >= 1e-3f) gp2 += -s / (a * a);
+          if (zb >= 1e-3f) gwc2 += s / (bb * bb);
+        } else if (cfg.disp_mode == 1) {
+          float a = fmaxf(za, 1e-3f), bb = fmaxf(zb, 1e-3f);
+          // max(a,b)/min(a,b) - 1
+          float ga, gb;
+          if (a >= bb) { ga = 1.0f / bb; gb = -a / (bb * bb); }
+          else         { ga = -bb / (a * a); gb = 1.0f / a; }
+          if (za >= 1e-3f) gp2 += ga * mc;
+          if (zb >= 1e-3f) gwc2 += gb * mc;
+        } else {
+          float s = sgn(za - zb) * mc;
+          gp2 += s;
+          gwc2 -= s;
+        }
+      } else {
+        float mc = m * cd;
+        ge0 = mc * sgn(o.wP2[0] - o.P1[0] - sx[v]);
+        ge1 = mc * sgn(o.wP2[1] - o.P1[1] - sy[v]);
+        ge2 = mc * sgn(o.wP2[2] - o.P1[2] - sz[v]);
+        // wP2 = sum_k w_k (R2 p2c2_k + t2)  =>  g_wpc += R2^T g_e
+        float a0, a1, a2;
+        mtv(ps.R2, ge0, ge1, ge2, a0, a1, a2);
+        gwc0 += a0; gwc1 += a1; gwc2 += a2;
+      }
+      // g_(P1 + sf) = R2 g_p12 ; sf_loss adds -g_e to both P1 and sf
+      float gv0, gv1, gv2;
+      mv(ps.R2, gp0, gp1, gp2, gv0, gv1, gv2);
+      ox[v] = gv0 - ge0; oy[v] = gv1 - ge1; oz[v] = gv2 - ge2;
+      // scatter to depth_2: p2c2_k = d2_k * ray_k
+      if (gd2img) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float w = tp.w[k];
+          float tx, ty, tz;
+          ray_of(ps.Kinv, tp.ux[k & 1], tp.uy[k >> 1], tx, ty, tz);
+          float g = w * fmaf(gwc2, tz, fmaf(gwc1, ty, gwc0 * tx));
+          if (g != 0.f) atomicAdd(gd2img + tp.idx[k], g);
+        }
+      }
+    }
+    float* gs = g_sf + (size_t)b * 3 * HW + pix;
+    store_vec<VEC>(gs, ox);
+    store_vec<VEC>(gs + HW, oy);
+    store_vec<VEC>(gs + 2 * (size_t)HW, oz);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// materialise every per-pixel tensor of the two reference modules (not on the training fast path)
+__global__ void __launch_bounds__(kThreads) reproject_materialize_kernel(
+    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
+    const float* __restrict__ sf, const float* __restrict__ poses, float* __restrict__ global_p1,
+    float* __restrict__ sf_by_depth, float* __restrict__ warped_global_p2, float* __restrict__ warped_p2_camera_2,
+    float* __restrict__ p1_camera_2, float* __restrict__ dflow, float* __restrict__ staticflow,
+    float* __restrict__ depth_image, float* __restrict__ depth_warp, int H, int W) {
+  __shared__ Pose ps;
+  const int b = blockIdx.y;
+  load_pose(ps, poses, b);
+  __syncthreads();
+  const int HW = H * W;
+  const float* d2img = depth_2 + (size_t)b * HW;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    int y = pix / W, xi = pix - y * W;
+    float x = (float)xi, yf = (float)y;
+    float d1 = depth_1[(size_t)b * HW + pix];
+    float2 f = *reinterpret_cast<const float2*>(flow + ((size_t)b * HW + pix) * 2);
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (sf) {
+      const float* sfp = sf + (size_t)b * 3 * HW + pix;
+      sx = sfp[0]; sy = sfp[HW]; sz = sfp[2 * (size_t)HW];
+    }
+    Taps tp = make_taps(x + f.x, yf + f.y, H, W);
+    Px o, os;
+    forward_px<true>(ps, d2img, tp, x, yf, d1, sx, sy, sz, o);
+    size_t o3 = (size_t)b * 3 * HW + pix, o2 = (size_t)b * 2 * HW + pix, o1 = (size_t)b * HW + pix;
+    if (global_p1) { global_p1[o3] = o.P1[0]; global_p1[o3 + HW] = o.P1[1]; global_p1[o3 + 2 * (size_t)HW] = o.P1[2]; }
+    if (sf_by_depth) {
+      sf_by_depth[o3] = o.wP2[0] - o.P1[0];
+      sf_by_depth[o3 + HW] = o.wP2[1] - o.P1[1];
+      sf_by_depth[o3 + 2 * (size_t)HW] = o.wP2[2] - o.P1[2];
+    }
+    if (warped_global_p2) { warped_global_p2[o3] = o.wP2[0]; warped_global_p2[o3 + HW] = o.wP2[1]; warped_global_p2[o3 + 2 * (size_t)HW] = o.wP2[2]; }
+    if (warped_p2_camera_2) { warped_p2_camera_2[o3] = o.wpc[0]; warped_p2_camera_2[o3 + HW] = o.wpc[1]; warped_p2_camera_2[o3 + 2 * (size_t)HW] = o.wpc[2]; }
+    if (p1_camera_2) { p1_camera_2[o3] = o.p12[0]; p1_camera_2[o3 + HW] = o.p12[1]; p1_camera_2[o3 + 2 * (size_t)HW] = o.p12[2]; }
+    if (dflow) { dflow[o2] = o.dflow[0]; dflow[o2 + HW] = o.dflow[1]; }
+    if (depth_image) depth_image[o1] = o.i12[2];
+    if (depth_warp) depth_warp[o1] = o.wd;
+    if (staticflow) {
+      forward_px<false>(ps, d2img, tp, x, yf, d1, 0.f, 0.f, 0.f, os);
+      staticflow[o2] = os.dflow[0];
+      staticflow[o2 + HW] = os.dflow[1];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs) {
+  bool al = true;
+  for (const void* p : ptrs) al = al && (p == nullptr || aligned16(p));
+  long total = (long)B * H * W;
+  // wide vectors only when enough threads remain to cover HBM latency (>= 512 / 256 threads per SM)
+  if (al && W % 4 == 0 && total / 4 >= (long)num_sms() * 512) return 4;
+  if (al && W % 2 == 0 && total / 2 >= (long)num_sms() * 256) return 2;
+  return 1;
+}
+
+static dim3 grid_for(int B, int items_per_pair) {
+  int per_pair = (items_per_pair + kThreads - 1) / kThreads;
+  int cap = (num_sms() * 8 + B - 1) / B;  // ~8 resident CTAs of 256 threads per SM over the whole grid
+  if (cap < 1) cap = 1;
+  if (per_pair > cap) per_pair = cap;
+  if (per_pair < 1) per_pair = 1;
+  return dim3((unsigned)per_pair, (unsigned)B, 1);
+}
+
+static int check_shape(int B, int H, int W) {
+  DVD_ARG_CHECK(B >= 1 && H >= 2 && W >= 2, "bad shape B=%d H=%d W=%d (need B>=1, H,W>=2)", B, H, W);
+  DVD_ARG_CHECK(B <= 65535, "B=%d exceeds gridDim.y", B);
+  DVD_ARG_CHECK((long)H * W < (1L << 30), "image too large");
+  return 0;
+}
+
+}  // namespace dvd
+
+using namespace dvd;
+
+extern "C" int dvd_reproject_partials_size(int B, int H, int W) {
+  if (B < 1 || H < 1 || W < 1) return 0;
+  // upper bound over every VEC choice
+  dim3 g = grid_for(B, H * W);
+  return (int)(g.x * g.y * 4);
+}
+
+extern "C" int dvd_unproject_fwd(const float* depth, const float* poses, float* P, int B, int H, int W, int which,
+                                 void* stream) {
+  if (int e = check_shape(B, H, W)) return e;
+  DVD_ARG_CHECK(depth && poses && P, "null pointer");
+  DVD_ARG_CHECK(which == 1 || which == 2, "which must be 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  int vec = pick_vec(B, H, W, {depth, P});
+  dim3 g = grid_for(B, H * W / vec);
+  if (vec == 4) unproject_fwd_kernel<4><<<g, kThreads, 0, st>>>(depth, poses, P, H, W, which);
+  else if (vec == 2) unproject_fwd_kernel<2><<<g, kThreads, 0, st>>>(depth, poses, P, H, W, which);
+  else unproject_fwd_kernel<1><<<g, kThreads, 0, st>>>(depth, poses, P, H, W, which);
+  DVD_CUDA_LAUNCH_CHECK("unproject_fwd");
+  return 0;
+}
+
+extern "C" int dvd_unproject_bwd(const float* gP, const float* poses, float* gdepth, int B, int H, int W, int which,
+                                 void* stream) {
+  if (int e = check_shape(B, H, W)) return e;
+  DVD_ARG_CHECK(gP && poses && gdepth, "null pointer");
+  DVD_ARG_CHECK(which == 1 || which == 2, "which must be 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  int vec = pick_vec(B, H, W, {gP, gdepth});
+  dim3 g = grid_for(B, H * W / vec);
+  if (vec == 4) unproject_bwd_kernel<4><<<g, kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
+  else if (vec == 2) unproject_bwd_kernel<2><<<g, kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
+  else unproject_bwd_kernel<1><<<g, kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
+  DVD_CUDA_LAUNCH_CHECK("unproject_bwd");
+  return 0;
+}
+
+static int check_cfg(const dvd_loss_cfg* cfg) {
+  DVD_ARG_CHECK(cfg != nullptr, "null loss cfg");
+  DVD_ARG_CHECK(cfg->disp_mode >= 0 && cfg->disp_mode <= 2, "disp_mode must be 0,1,2");
+  return 0;
+}
+
+extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2, const float* flow_1_2,
+                                      const float* mask_2, const float* sf, const float* poses,
+                                      const dvd_loss_cfg* cfg, float* partials, float* scalars, int B, int H,
+                                      int W, void* stream) {
+  if (int e = check_shape(B, H, W)) return e;
+  if (int e = check_cfg(cfg)) return e;
+  DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && mask_2 && sf && poses && partials && scalars, "null pointer");
+  DVD_ARG_CHECK(aligned16(partials), "partials must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2});
+  dim3 g = grid_for(B, H * W / vec);
+  if (vec == 4) reproject_loss_fwd_kernel<4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+  else if (vec == 2) reproject_loss_fwd_kernel<2><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+  else reproject_loss_fwd_kernel<1><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+  DVD_CUDA_LAUNCH_CHECK("reproject_loss_fwd");
+  reproject_finalize_kernel<<<1, 256, 0, st>>>(partials, (int)(g.x * g.y), *cfg, scalars);
+  DVD_CUDA_LAUNCH_CHECK("reproject_finalize");
+  return 0;
+}
+
+extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2, const float* flow_1_2,
+                                      const float* mask_2, const float* sf, const float* poses,
+                                      const dvd_loss_cfg* cfg, const float* scalars, float gscale, const float* gscale_dev,
+                                      float* g_sf, float* g_depth_2, int B, int H, int W, void* stream) {
+  if (int e = check_shape(B, H, W)) return e;
+  if (int e = check_cfg(cfg)) return e;
+  DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && mask_2 && sf && poses && scalars && g_sf, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_depth_2) DVD_CUDA_CALL(cudaMemsetAsync(g_depth_2, 0, (size_t)B * H * W * sizeof(float), st));
+  int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2, g_sf});
+  dim3 g = grid_for(B, H * W / vec);
+  if (vec == 4) reproject_loss_bwd_kernel<4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
+  else if (vec == 2) reproject_loss_bwd_kernel<2><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
+  else reproject_loss_bwd_kernel<1><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
+  DVD_CUDA_LAUNCH_CHECK("reproject_loss_bwd");
+  return 0;
+}
+
+extern "C" int dvd_reproject_materialize(const float* depth_1, const float* depth_2, const float* flow_1_2,
+                                         const float* sf, const float* poses, float* global_p1, float* sf_by_depth,
+                                         float* warped_global_p2, float* warped_p2_camera_2, float* p1_camera_2,
+                                         float* dflow_1_2, float* staticflow_1_2, float* depth_image_1_2,
+                                         float* depth_warp_1_2, int B, int H, int W, void* stream) {
+  if (int e = check_shape(B, H, W)) return e;
+  DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && poses, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 g = grid_for(B, H * W);
+  reproject_materialize_kernel<<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, sf, poses, global_p1, sf_by_depth,
+                                                       warped_global_p2, warped_p2_camera_2, p1_camera_2, dflow_1_2,
+                                                       staticflow_1_2, depth_image_1_2, depth_warp_1_2, H, W);
+  DVD_CUDA_LAUNCH_CHECK("reproject_materialize");
+  return 0;
+}

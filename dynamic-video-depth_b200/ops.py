@@ -1,0 +1,203 @@
+"""Python face of the C ABI: argument checks, output allocation, autograd wiring.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); all arithmetic of the hot path
+happens inside libdvd_b200.so. Argument / shape / dtype / contiguity violations raise ValueError
+before any launch; a non-zero return from the library raises RuntimeError.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import LossCfg
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _chk(t, name, shape=None):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError('%s must be a torch.Tensor' % name)
+    if not t.is_cuda:
+        raise ValueError('%s must live on a CUDA device (dvd_b200 has no CPU path)' % name)
+    if t.dtype != torch.float32:
+        raise ValueError('%s must be float32, got %s' % (name, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError('%s has shape %s, expected %s' % (name, tuple(t.shape), tuple(shape)))
+    return t
+
+
+def make_loss_cfg(midas=True, warm=False, use_disp=True, use_disp_ratio=False, flow_mul=1.0, disp_mul=1.0):
+    """Flags → struct dvd_loss_cfg (models/scene_flow_motion_field.py:140-150,285-319)."""
+    mode = 0 if use_disp else (1 if use_disp_ratio else 2)
+    return LossCfg(int(bool(midas)), int(bool(warm)), mode, int(bool(use_disp)), float(flow_mul), float(disp_mul))
+
+
+def pack_poses(K, K_inv, R_1_T, R_2_T, t_1, t_2):
+    """Reference-format pose tensors → [B,48] pose blocks of the C ABI.
+
+    The reference stores transposes for row-vector algebra: K = K^T, K_inv = (K^-1)^T,
+    R_i_T = R_c2w_i (scripts/preprocess/davis/generate_sequence_midas.py:61-76). Accepts the
+    [B,1,1,3,3] / [B,1,1,1,3] shapes of the batch dict (or anything reshapeable to [B,3,3] / [B,3])."""
+    B = K.reshape(-1, 3, 3).shape[0]
+    Kc = K.reshape(B, 3, 3).transpose(1, 2)
+    Ki = K_inv.reshape(B, 3, 3).transpose(1, 2)
+    out = torch.zeros(B, 48, dtype=torch.float32, device=K.device)
+    out[:, 0:9] = Ki.reshape(B, 9)
+    out[:, 9:18] = Kc.reshape(B, 9)
+    out[:, 18:27] = R_1_T.reshape(B, 9)
+    out[:, 27:36] = R_2_T.reshape(B, 9)
+    out[:, 36:39] = t_1.reshape(B, 3)
+    out[:, 39:42] = t_2.reshape(B, 3)
+    return out
+
+
+def pack_poses_from_batch(batch):
+    return pack_poses(batch['K'], batch['K_inv'], batch['R_1_T'], batch['R_2_T'], batch['t_1'], batch['t_2'])
+
+
+# ------------------------------------------------------------------------------------------------
+# raw calls (no autograd)
+
+def unproject_fwd(depth, poses, which=1):
+    B, C, H, W = depth.shape
+    _chk(depth, 'depth', (B, 1, H, W)), _chk(poses, 'poses', (B, 48))
+    P = torch.empty(B, 3, H, W, dtype=torch.float32, device=depth.device)
+    lib = _lib.load()
+    _lib.check(lib.dvd_unproject_fwd(_ptr(depth), _ptr(poses), _ptr(P), B, H, W, int(which), _stream()),
+               'dvd_unproject_fwd')
+    return P
+
+
+def unproject_bwd(gP, poses, which=1):
+    B, C, H, W = gP.shape
+    _chk(gP, 'gP', (B, 3, H, W)), _chk(poses, 'poses', (B, 48))
+    gd = torch.empty(B, 1, H, W, dtype=torch.float32, device=gP.device)
+    lib = _lib.load()
+    _lib.check(lib.dvd_unproject_bwd(_ptr(gP), _ptr(poses), _ptr(gd), B, H, W, int(which), _stream()),
+               'dvd_unproject_bwd')
+    return gd
+
+
+def _chk_reproject(depth_1, depth_2, flow, mask, sf, poses):
+    if depth_1.dim() != 4:
+        raise ValueError('depth_1 must be [B,1,H,W]')
+    B, _, H, W = depth_1.shape
+    _chk(depth_1, 'depth_1', (B, 1, H, W)), _chk(depth_2, 'depth_2', (B, 1, H, W))
+    _chk(flow, 'flow_1_2', (B, H, W, 2)), _chk(poses, 'poses', (B, 48))
+    if mask is not None:
+        _chk(mask, 'mask_2')
+        if mask.numel() != B * H * W:
+            raise ValueError('mask_2 must have B*H*W elements')
+    if sf is not None:
+        _chk(sf, 'sf', (B, 3, H, W))
+    return B, H, W
+
+
+def reproject_loss_fwd(depth_1, depth_2, flow, mask, sf, poses, cfg):
+    """→ scalars [8] (see enum in include/dvd_b200.h): flow, disp, sf, loss, mask-sum, cf, cd, 0."""
+    B, H, W = _chk_reproject(depth_1, depth_2, flow, mask, sf, poses)
+    lib = _lib.load()
+    n = lib.dvd_reproject_partials_size(B, H, W)
+    partials = torch.empty(n, dtype=torch.float32, device=depth_1.device)
+    scalars = torch.empty(8, dtype=torch.float32, device=depth_1.device)
+    _lib.check(lib.dvd_reproject_loss_fwd(_ptr(depth_1), _ptr(depth_2), _ptr(flow), _ptr(mask), _ptr(sf), _ptr(poses),
+                                          ctypes.byref(cfg), _ptr(partials), _ptr(scalars), B, H, W, _stream()),
+               'dvd_reproject_loss_fwd')
+    return scalars
+
+
+def reproject_loss_bwd(depth_1, depth_2, flow, mask, sf, poses, cfg, scalars, gscale=1.0, gscale_dev=None,
+                       need_depth_grad=True):
+    B, H, W = _chk_reproject(depth_1, depth_2, flow, mask, sf, poses)
+    _chk(scalars, 'scalars', (8,))
+    g_sf = torch.empty_like(sf)
+    g_d2 = torch.empty_like(depth_2) if need_depth_grad else None
+    lib = _lib.load()
+    _lib.check(lib.dvd_reproject_loss_bwd(_ptr(depth_1), _ptr(depth_2), _ptr(flow), _ptr(mask), _ptr(sf), _ptr(poses),
+                                          ctypes.byref(cfg), _ptr(scalars), float(gscale), _ptr(gscale_dev),
+                                          _ptr(g_sf), _ptr(g_d2), B, H, W, _stream()),
+               'dvd_reproject_loss_bwd')
+    return g_sf, g_d2
+
+
+_MAT_KEYS3 = ('global_p1', 'sf_by_depth', 'warped_global_p2', 'warped_p2_camera_2', 'p1_camera_2')
+_MAT_KEYS2 = ('dflow_1_2', 'staticflow_1_2')
+_MAT_KEYS1 = ('depth_image_1_2', 'depth_warp_1_2')
+
+
+def reproject_materialize(depth_1, depth_2, flow, sf, poses, keys=None):
+    """Per-pixel tensors of flow_by_depth / scene_flow_projection_slack, channel-planar."""
+    B, H, W = _chk_reproject(depth_1, depth_2, flow, None, sf, poses)
+    allk = _MAT_KEYS3 + _MAT_KEYS2 + _MAT_KEYS1
+    keys = allk if keys is None else keys
+    out = {}
+    for k in allk:
+        if k in keys:
+            c = 3 if k in _MAT_KEYS3 else (2 if k in _MAT_KEYS2 else 1)
+            out[k] = torch.empty(B, c, H, W, dtype=torch.float32, device=depth_1.device)
+    lib = _lib.load()
+    _lib.check(lib.dvd_reproject_materialize(_ptr(depth_1), _ptr(depth_2), _ptr(flow), _ptr(sf), _ptr(poses),
+                                             *[_ptr(out.get(k)) for k in allk], B, H, W, _stream()),
+               'dvd_reproject_materialize')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd wiring
+
+class Unproject(torch.autograd.Function):
+    """unproject_ptcld.forward (losses/scene_flow_projection.py:48-67) → [B,3,H,W]."""
+
+    @staticmethod
+    def forward(ctx, depth, poses, which):
+        ctx.save_for_backward(poses)
+        ctx.which = which
+        return unproject_fwd(depth.contiguous(), poses, which)
+
+    @staticmethod
+    def backward(ctx, gP):
+        (poses,) = ctx.saved_tensors
+        return unproject_bwd(gP.contiguous(), poses, ctx.which), None, None
+
+
+def unproject(depth, poses, which=1):
+    return Unproject.apply(depth, poses, which)
+
+
+class ReprojectLoss(torch.autograd.Function):
+    """Fused W1+W2+L1. Returns (loss, scalars[8]); only `loss` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, depth_1, depth_2, sf, flow, mask, poses, cfg, gscale):
+        depth_1, depth_2, sf = depth_1.contiguous(), depth_2.contiguous(), sf.contiguous()
+        scalars = reproject_loss_fwd(depth_1, depth_2, flow, mask, sf, poses, cfg)
+        ctx.save_for_backward(depth_1, depth_2, sf, flow, mask, poses, scalars)
+        ctx.cfg, ctx.gscale = cfg, gscale
+        ctx.need_depth = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        loss = scalars[3] * gscale if gscale != 1.0 else scalars[3].clone()
+        ctx.mark_non_differentiable(scalars)
+        return loss, scalars
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_scalars):
+        depth_1, depth_2, sf, flow, mask, poses, scalars = ctx.saved_tensors
+        g = g_loss.contiguous().to(torch.float32)
+        g_sf, g_d2 = reproject_loss_bwd(depth_1, depth_2, flow, mask, sf, poses, ctx.cfg, scalars,
+                                        gscale=ctx.gscale, gscale_dev=g, need_depth_grad=ctx.need_depth)
+        g_d1 = None
+        if ctx.needs_input_grad[0]:
+            # global_p1 and sf enter the chain only as P1 + sf  =>  dL/dP1 == dL/dsf
+            g_d1 = unproject_bwd(g_sf, poses, 1)
+        return g_d1, (g_d2 if ctx.needs_input_grad[1] else None), g_sf, None, None, None, None, None
+
+
+def reproject_loss(depth_1, depth_2, sf, flow, mask, poses, cfg, gscale=1.0):
+    return ReprojectLoss.apply(depth_1, depth_2, sf, flow, mask, poses, cfg, float(gscale))

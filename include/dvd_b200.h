@@ -1,0 +1,97 @@
+/*
+ * dvd_b200.h — C ABI of libdvd_b200.so (B200 / sm_100a hot path of google/dynamic-video-depth).
+ *
+ * The reference has NO native boundary on this path: it is Python over ATen
+ * (last row). These entry points are what a maintainer binds from the
+ * reference's Python modules with ctypes; each one names the reference
+ * code it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a caller-allocated, contiguous fp32 buffer
+ *     (16-byte aligned unless noted); nothing is allocated or freed by the library, no ownership moves;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises;
+ *   - return value: 0 on success, negative = argument error, positive = cudaError_t;
+ *     dvd_last_error() returns a thread-local message for the last non-zero return;
+ *   - image tensors are channel-planar [B,C,H,W]; optical flow is [B,H,W,2]; masks are [B,H,W].
+ *   - `poses` is [B,48] fp32: Kinv[9] K[9] R1[9] R2[9] t1[3] t2[3] pad[6], matrices row-major in
+ *     COLUMN-vector convention (R = camera-to-world). The reference stores the transposes
+ *     (scripts/preprocess/davis/generate_sequence_midas.py:61-76); dvd_b200.ops.pack_poses converts.
+ */
+#ifndef DVD_B200_H_
+#define DVD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVD_POSE_STRIDE 48
+
+/* loss configuration — mirrors the live flags of models/scene_flow_motion_field.py:33-67,285-324 */
+typedef struct dvd_loss_cfg {
+  int   midas;          /* 1: mask *= [d1<100]·[warped z<100]   (smf.py:286-289) */
+  int   warm;           /* 1: L2 flow criterion (epoch <= warm_sf), 0: L1  (smf.py:291) */
+  int   disp_mode;      /* 0: --use_disp, 1: --use_disp_ratio, 2: |z1 - z2|  (smf.py:140-150) */
+  int   second_is_disp; /* 1: loss uses disp_loss (--use_disp), 0: uses sf_loss (smf.py:310-319) */
+  float flow_mul;       /* --flow_mul */
+  float disp_mul;       /* --disp_mul */
+} dvd_loss_cfg;
+
+/* scalars written by dvd_reproject_loss_fwd (device, 8 floats) */
+enum { DVD_S_FLOW = 0, DVD_S_DISP = 1, DVD_S_SF = 2, DVD_S_LOSS = 3, DVD_S_MASKSUM = 4,
+       DVD_S_CF = 5 /* flow_mul/N */, DVD_S_CD = 6 /* disp_mul/N */, DVD_S_RSVD = 7 };
+
+const char* dvd_last_error(void);
+int dvd_version(void);
+/* number of fp32 partial-sum slots dvd_reproject_loss_fwd needs in `partials` for a given shape */
+int dvd_reproject_partials_size(int B, int H, int W);
+
+/* W3  unproject_ptcld.forward  (losses/scene_flow_projection.py:48-67):  P = R·(d·Kinv·c) + t
+ * which = 1 uses (R1,t1), which = 2 uses (R2,t2).  depth [B,1,H,W] -> P [B,3,H,W]            */
+int dvd_unproject_fwd(const float* depth, const float* poses, float* P,
+                      int B, int H, int W, int which, void* stream);
+/* adjoint: gP [B,3,H,W] -> gdepth [B,1,H,W]  (overwrites) */
+int dvd_unproject_bwd(const float* gP, const float* poses, float* gdepth,
+                      int B, int H, int W, int which, void* stream);
+
+/* W1+W2+L1 fused forward: flow_by_depth.forward + scene_flow_projection_slack.forward
+ * (losses/scene_flow_projection.py:95-153,204-278) + Model._calc_loss
+ * (models/scene_flow_motion_field.py:285-324) without materialising any per-pixel tensor.
+ *   depth_1, depth_2 [B,1,H,W]; flow_1_2 [B,H,W,2]; mask_2 [B,H,W]; sf [B,3,H,W]
+ *   partials: scratch, dvd_reproject_partials_size() floats; scalars: 8 floats (enum above). */
+int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2, const float* flow_1_2,
+                           const float* mask_2, const float* sf, const float* poses,
+                           const dvd_loss_cfg* cfg, float* partials, float* scalars,
+                           int B, int H, int W, void* stream);
+
+/* adjoint of the above w.r.t. sf (== w.r.t. global_p1, both enter only as P1+sf) and depth_2.
+ *   g_sf [B,3,H,W] overwritten; g_depth_2 [B,1,H,W] zero-filled then scatter-added (may be NULL
+ *   when the depth net is frozen — warm-up phase, smf.py:154-164). The upstream gradient is
+ *   gscale (host, e.g. `steps` for --weight_steps, smf.py:189-190) times *gscale_dev (device
+ *   scalar, may be NULL = 1) so autograd's grad_output never needs a host read-back.          */
+int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2, const float* flow_1_2,
+                           const float* mask_2, const float* sf, const float* poses,
+                           const dvd_loss_cfg* cfg, const float* scalars, float gscale,
+                           const float* gscale_dev, float* g_sf, float* g_depth_2,
+                           int B, int H, int W, void* stream);
+
+/* materialise every per-pixel tensor the two reference modules return (visualised batches and the
+ * operator-level drop-in). Any output pointer may be NULL. All channel-planar:
+ *   global_p1, sf_by_depth, warped_global_p2, warped_p2_camera_2, p1_camera_2 : [B,3,H,W]
+ *   dflow_1_2, staticflow_1_2 : [B,2,H,W];  depth_image_1_2, depth_warp_1_2 : [B,1,H,W]      */
+int dvd_reproject_materialize(const float* depth_1, const float* depth_2, const float* flow_1_2,
+                              const float* sf, const float* poses,
+                              float* global_p1, float* sf_by_depth, float* warped_global_p2,
+                              float* warped_p2_camera_2, float* p1_camera_2, float* dflow_1_2,
+                              float* staticflow_1_2, float* depth_image_1_2, float* depth_warp_1_2,
+                              int B, int H, int W, void* stream);
+
+/* ---- scene-flow MLP (M1-M4, L2): networks/blocks.py:19-34, networks/sceneflow_field.py:20-53,
+ *      models/scene_flow_motion_field.py:326-367 — declared in the MLP section below ---------- */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVD_B200_H_ */
