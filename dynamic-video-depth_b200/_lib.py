@@ -37,6 +37,7 @@ SIGNATURES = {
     'dvd_reproject_loss_fwd': [_P, _P, _P, _P, _P, _P, ctypes.POINTER(LossCfg), _P, _P, _I, _I, _I, _P],
     'dvd_reproject_loss_bwd': [_P, _P, _P, _P, _P, _P, ctypes.POINTER(LossCfg), _P, _F, _P, _P, _P, _I, _I, _I, _P],
     'dvd_reproject_materialize': [_P] * 14 + [_I, _I, _I, _P],
+    'dvd_selftest_umma': [_P, _P, _P, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'dvd_last_error': ctypes.c_char_p}
 

@@ -1,0 +1,136 @@
+// Self-test of the tcgen05 building blocks (descriptors, SS / TS operand modes, bf16x3 split,
+// TMEM load/store, commit -> mbarrier). One CTA computes D[128,N] = A[128,K] * B[N,K]^T with the
+// same primitives the scene-flow MLP kernels use; the host compares against an fp32 GEMM.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace dvd {
+using namespace tc;
+
+// mode 0: A from shared memory (SS), mode 1: A from tensor memory (TS). passes: 1 (bf16) or 3 (bf16x3)
+__global__ void __launch_bounds__(160, 1) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                               float* __restrict__ D, int K, int N, int mode, int passes) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms must start on 1024-byte boundaries of the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_holder;
+  const int nchunk = K / 64;
+  // smem carve-up: per chunk: A_hi (16 KB) A_lo (16 KB) B_hi (N*128) B_lo (N*128)
+  const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)N * 128;
+  uint8_t* sA_hi = smem;
+  uint8_t* sA_lo = sA_hi + nchunk * a_bytes;
+  uint8_t* sB_hi = sA_lo + nchunk * a_bytes;
+  uint8_t* sB_lo = sB_hi + nchunk * b_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4) {
+    tmem_alloc(&tmem_base_holder, 512);
+    if (lane == 0) {
+      mbar_init(&bar_done, 1);
+      fence_mbar_init();
+    }
+  }
+  // fill shared-memory operand images (generic proxy writes)
+  for (int i = threadIdx.x; i < 128 * K / 2; i += blockDim.x) {
+    int row = i / (K / 2), k = (i % (K / 2)) * 2;
+    uint32_t hi, lo;
+    split2(A[row * K + k], A[row * K + k + 1], hi, lo);
+    uint32_t off = (k / 64) * a_bytes + sw128_offset(row, k % 64);
+    *reinterpret_cast<uint32_t*>(sA_hi + off) = hi;
+    *reinterpret_cast<uint32_t*>(sA_lo + off) = lo;
+  }
+  for (int i = threadIdx.x; i < N * K / 2; i += blockDim.x) {
+    int row = i / (K / 2), k = (i % (K / 2)) * 2;
+    uint32_t hi, lo;
+    split2(B[row * K + k], B[row * K + k + 1], hi, lo);
+    uint32_t off = (k / 64) * b_bytes + sw128_offset(row, k % 64);
+    *reinterpret_cast<uint32_t*>(sB_hi + off) = hi;
+    *reinterpret_cast<uint32_t*>(sB_lo + off) = lo;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_holder;
+  const uint32_t tD = tmem;             // columns [0, N)
+  const uint32_t tA_hi = tmem + 256;    // packed bf16: K/2 columns
+  const uint32_t tA_lo = tmem + 384;
+
+  if (mode == 1 && warp < 4) {
+    // A operand into tensor memory: thread = row, 32-bit column j holds elements (2j, 2j+1)
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t h[16], l[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) split2(A[row * K + 2 * (c0 + j)], A[row * K + 2 * (c0 + j) + 1], h[j], l[j]);
+      tmem_st16(tA_hi + lane_base + c0, h);
+      tmem_st16(tA_lo + lane_base + c0, l);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 4 && lane == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    uint32_t acc = 0;
+    for (int p = 0; p < passes; ++p) {
+      // p = 0: hi*hi, 1: lo(A)*hi(B), 2: hi(A)*lo(B)
+      const uint8_t* a_img = (p == 1) ? sA_lo : sA_hi;
+      const uint32_t a_tm = (p == 1) ? tA_lo : tA_hi;
+      const uint8_t* b_img = (p == 2) ? sB_lo : sB_hi;
+      for (int kc = 0; kc < nchunk; ++kc) {
+        for (int ks = 0; ks < 4; ++ks) {  // 16 bf16 = 32 bytes per MMA
+          uint64_t bd = make_sdesc_k_sw128(smem_u32(b_img + kc * b_bytes) + ks * 32);
+          if (mode == 0) {
+            uint64_t ad = make_sdesc_k_sw128(smem_u32(a_img + kc * a_bytes) + ks * 32);
+            umma_ss(tD, ad, bd, idesc, acc);
+          } else {
+            umma_ts(tD, a_tm + (kc * 4 + ks) * 8, bd, idesc, acc);
+          }
+          acc = 1;
+        }
+      }
+    }
+    umma_commit(&bar_done);
+  }
+  if (warp < 4) {
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tD + lane_base + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) D[row * N + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace dvd
+
+// A [128,K] fp32 row-major, B [N,K] fp32 row-major, D [128,N] fp32; K in {64,128}, N in {16..256, %16}
+extern "C" int dvd_selftest_umma(const float* A, const float* B, float* D, int K, int N, int mode, int passes,
+                                 void* stream) {
+  DVD_ARG_CHECK(A && B && D, "null pointer");
+  DVD_ARG_CHECK(K == 64 || K == 128, "K must be 64 or 128");
+  DVD_ARG_CHECK(N >= 16 && N <= 256 && N % 16 == 0, "N must be a multiple of 16 in [16,256]");
+  DVD_ARG_CHECK(mode == 0 || mode == 1, "mode 0 (SS) or 1 (TS)");
+  DVD_ARG_CHECK(passes == 1 || passes == 3, "passes 1 or 3");
+  size_t smem = (size_t)(K / 64) * 2 * (128 * 128 + (size_t)N * 128) + 1024;
+  DVD_CUDA_CALL(cudaFuncSetAttribute(dvd::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dvd::umma_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, D, K, N, mode, passes);
+  DVD_CUDA_LAUNCH_CHECK("umma_selftest");
+  return 0;
+}

@@ -88,6 +88,12 @@ int dvd_reproject_materialize(const float* depth_1, const float* depth_2, const 
                               float* staticflow_1_2, float* depth_image_1_2, float* depth_warp_1_2,
                               int B, int H, int W, void* stream);
 
+/* self-test of the tcgen05 building blocks (one CTA): D[128,N] = A[128,K]·B[N,K]^T, fp32 row-major
+ * in/out, K in {64,128}, N multiple of 16 <= 256; mode 0 = A from shared memory, 1 = A from tensor
+ * memory; passes 1 = bf16, 3 = bf16x3 split (fp32-grade). Not on the hot path.                 */
+int dvd_selftest_umma(const float* A, const float* B, float* D, int K, int N, int mode, int passes,
+                      void* stream);
+
 /* ---- scene-flow MLP (M1-M4, L2): networks/blocks.py:19-34, networks/sceneflow_field.py:20-53,
  *      models/scene_flow_motion_field.py:326-367 — declared in the MLP section below ---------- */
 

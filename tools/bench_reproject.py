@@ -1,0 +1,62 @@
+"""Micro-benchmark of the fused re-projection kernels (CUDA events, L2 flushed between iterations).
+Algorithmic bytes/pixel: unproject fwd 16, fused fwd 32, fused bwd 48, unproject bwd 16."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def timeit(fn, iters=20, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main(B=64, H=224, W=384):
+    from dvd_b200 import ops, synthetic
+    dev = 'cuda'
+    one = synthetic.make_batch([(4, 8)], H=H, W=W, seed=0, leading_dim=False)
+    rep = lambda t: t.to(dev).repeat(B, *([1] * (t.dim() - 1))).contiguous()  # noqa: E731
+    flow, mask = rep(one['flow_1_2']), rep(one['mask_2'].reshape(1, H, W))
+    poses = rep(ops.pack_poses_from_batch({k: v for k, v in one.items() if torch.is_tensor(v)}))
+    d1, d2 = rep(synthetic.make_depths(1, H, W, seed=1)), rep(synthetic.make_depths(1, H, W, seed=2))
+    sf = torch.randn(B, 3, H, W, device=dev) * 0.05
+    cfg = ops.make_loss_cfg()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    px = B * H * W
+    res = {}
+    scal = ops.reproject_loss_fwd(d1, d2, flow, mask, sf, poses, cfg)
+    P = ops.unproject_fwd(d1, poses, 1)
+    cases = {
+        'unproject_fwd': (lambda: ops.unproject_fwd(d1, poses, 1), 16),
+        'reproject_loss_fwd': (lambda: ops.reproject_loss_fwd(d1, d2, flow, mask, sf, poses, cfg), 32),
+        'reproject_loss_bwd': (lambda: ops.reproject_loss_bwd(d1, d2, flow, mask, sf, poses, cfg, scal), 48),
+        'unproject_bwd': (lambda: ops.unproject_bwd(P, poses, 1), 16),
+    }
+    for name, (fn, bpp) in cases.items():
+        med, best = timeit(fn, flush=flush)
+        res[name] = {'ms_median': med * 1e3, 'ms_best': best * 1e3, 'GBps_median': px * bpp / med / 1e9,
+                     'GBps_best': px * bpp / best / 1e9, 'bytes_per_px': bpp}
+        print(name, res[name], flush=True)
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump({'B': B, 'H': H, 'W': W, 'results': res}, open(os.path.join(ROOT, 'gpurun_out', 'bench_reproject.json'), 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main(B=int(sys.argv[1]) if len(sys.argv) > 1 else 64)
