@@ -18,10 +18,10 @@ class LossCfg(ctypes.Structure):
                 ('second_is_disp', ctypes.c_int), ('flow_mul', ctypes.c_float), ('disp_mul', ctypes.c_float)]
 
 
-class MlpDims(ctypes.Structure):
-    """struct dvd_mlp_dims (include/dvd_b200.h)."""
+class MlpCfg(ctypes.Structure):
+    """struct dvd_mlp_cfg (include/dvd_b200.h)."""
     _fields_ = [('n_freq_xyz', ctypes.c_int), ('n_freq_t', ctypes.c_int), ('time_dependent', ctypes.c_int),
-                ('width', ctypes.c_int), ('n_hidden', ctypes.c_int), ('out_scale', ctypes.c_float)]
+                ('sf_mag_div', ctypes.c_float), ('freq_xyz', ctypes.c_float * 16), ('freq_t', ctypes.c_float * 16)]
 
 
 _I, _F, _P = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
@@ -38,8 +38,20 @@ SIGNATURES = {
     'dvd_reproject_loss_bwd': [_P, _P, _P, _P, _P, _P, ctypes.POINTER(LossCfg), _P, _F, _P, _P, _P, _I, _I, _I, _P],
     'dvd_reproject_materialize': [_P] * 14 + [_I, _I, _I, _P],
     'dvd_selftest_umma': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'dvd_mlp_packed_weights_bytes': [ctypes.POINTER(MlpCfg)],
+    'dvd_mlp_save_bytes_per_eval': [ctypes.POINTER(MlpCfg), ctypes.c_long],
+    'dvd_mlp_dy_bytes': [ctypes.POINTER(MlpCfg), ctypes.c_long],
+    'dvd_mlp_pack_weights': [ctypes.POINTER(MlpCfg), ctypes.POINTER(ctypes.c_void_p), _P, _P, _P],
+    'dvd_mlp_chain_fwd': [ctypes.POINTER(MlpCfg), _P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P,
+                          ctypes.c_long, ctypes.c_long, _P],
+    'dvd_mlp_dgrad': [ctypes.POINTER(MlpCfg), _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P,
+                      ctypes.c_long, ctypes.c_long, _P],
+    'dvd_mlp_wgrad': [ctypes.POINTER(MlpCfg), _P, _P, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                      ctypes.c_long, _P],
+    'dvd_acc_reg': [_P, _P, _F, _F, _P, _P, _P, _P, ctypes.c_long, _P],
 }
-_RESTYPES = {'dvd_last_error': ctypes.c_char_p}
+_RESTYPES = {'dvd_last_error': ctypes.c_char_p, 'dvd_mlp_packed_weights_bytes': ctypes.c_size_t,
+             'dvd_mlp_save_bytes_per_eval': ctypes.c_size_t, 'dvd_mlp_dy_bytes': ctypes.c_size_t}
 
 _lib = None
 

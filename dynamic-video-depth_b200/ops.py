@@ -201,3 +201,165 @@ class ReprojectLoss(torch.autograd.Function):
 
 def reproject_loss(depth_1, depth_2, sf, flow, mask, poses, cfg, gscale=1.0):
     return ReprojectLoss.apply(depth_1, depth_2, sf, flow, mask, poses, cfg, float(gscale))
+
+
+# ================================================================================================
+# scene-flow MLP (tcgen05 kernels)
+
+from ._lib import MlpCfg  # noqa: E402
+
+
+def make_mlp_cfg(n_freq_xyz=16, n_freq_t=16, time_dependent=True, sf_mag_div=100.0):
+    """struct dvd_mlp_cfg; frequencies = torch.linspace(1, N+1, N) in fp32 exactly as
+    PeriodicEmbed builds them (networks/blocks.py:23-24)."""
+    if n_freq_xyz > 16 or n_freq_t > 16:
+        raise ValueError('n_freq_xyz / n_freq_t must be <= 16')
+    c = MlpCfg()
+    c.n_freq_xyz, c.n_freq_t, c.time_dependent, c.sf_mag_div = int(n_freq_xyz), int(n_freq_t), int(bool(time_dependent)), float(sf_mag_div)
+    fx = torch.linspace(1, n_freq_xyz + 1, steps=n_freq_xyz, dtype=torch.float32).tolist() if n_freq_xyz > 0 else []
+    ft = torch.linspace(1, n_freq_t + 1, steps=n_freq_t, dtype=torch.float32).tolist() if n_freq_t > 0 else []
+    for i in range(16):
+        c.freq_xyz[i] = fx[i] if i < len(fx) else 0.0
+        c.freq_t[i] = ft[i] if i < len(ft) else 0.0
+    return c
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+class PackedMlp:
+    """Device-side bf16 (hi,lo) UMMA images of the six weight matrices + the fp32 bias vector.
+    Re-pack after every optimiser step (`refresh`)."""
+
+    def __init__(self, cfg, device):
+        lib = _lib.load()
+        self.cfg = cfg
+        n = lib.dvd_mlp_packed_weights_bytes(ctypes.byref(cfg))
+        self.fwd = torch.empty(n, dtype=torch.uint8, device=device)
+        self.bwd = torch.empty(n, dtype=torch.uint8, device=device)
+        self.bias = torch.zeros(5 * 256 + 16, dtype=torch.float32, device=device)
+
+    def refresh(self, weights, biases):
+        """weights[l]: [out,in(,1,1)] fp32 contiguous cuda tensors, biases[l]: [out]."""
+        if len(weights) != 6 or len(biases) != 6:
+            raise ValueError('the scene-flow MLP has 6 layers')
+        ws = [_chk(w.detach(), 'weight[%d]' % i) for i, w in enumerate(weights)]
+        lib = _lib.load()
+        _lib.check(lib.dvd_mlp_pack_weights(ctypes.byref(self.cfg), _ptr_array(ws), _ptr(self.fwd), _ptr(self.bwd),
+                                            _stream()), 'dvd_mlp_pack_weights')
+        with torch.no_grad():
+            for l in range(5):
+                self.bias[l * 256:(l + 1) * 256].copy_(biases[l].detach())
+            self.bias[1280:1283].copy_(biases[5].detach())
+        return self
+
+
+def mlp_chain_fwd(packed, p0, t0, dt, n_eval, n_acc, save=False, want_steps=True):
+    """Raw forward. Returns dict(acc, s_steps, p_steps, save) (tensors or None)."""
+    cfg = packed.cfg
+    B, C, H, W = p0.shape
+    _chk(p0, 'p0', (B, 3, H, W))
+    if cfg.time_dependent:
+        _chk(t0, 't0', (B, 1, H, W))
+    npx, hw = B * H * W, H * W
+    dev = p0.device
+    lib = _lib.load()
+    acc = torch.empty_like(p0)
+    s_steps = torch.empty(n_eval, B, 3, H, W, dtype=torch.float32, device=dev) if (want_steps or save) else None
+    p_steps = sv = None
+    if save:
+        p_steps = torch.empty(n_eval, B, 3, H, W, dtype=torch.float32, device=dev)
+        per = lib.dvd_mlp_save_bytes_per_eval(ctypes.byref(cfg), npx)
+        sv = torch.empty(n_eval * per, dtype=torch.uint8, device=dev)
+    _lib.check(lib.dvd_mlp_chain_fwd(ctypes.byref(cfg), _ptr(packed.fwd), _ptr(packed.bias), _ptr(p0),
+                                     _ptr(t0) if cfg.time_dependent else ctypes.c_void_p(0), float(dt), int(n_eval),
+                                     int(n_acc), _ptr(acc), _ptr(s_steps), _ptr(p_steps), _ptr(sv), npx, hw, _stream()),
+               'dvd_mlp_chain_fwd')
+    return {'acc': acc, 's_steps': s_steps, 'p_steps': p_steps, 'save': sv}
+
+
+def mlp_chain_bwd(packed, fwd, t0, dt, n_acc, g_acc, g_steps, grad_w, grad_b):
+    """Raw backward over all evals: dgrad chain + wgrad per eval (descending).
+    g_acc [B,3,H,W] or None; g_steps: list (len n_eval) of [B,3,H,W] or None entries.
+    grad_w / grad_b: lists of 6 fp32 tensors ACCUMULATED into. Returns dL/dp0."""
+    cfg = packed.cfg
+    p_steps, sv = fwd['p_steps'], fwd['save']
+    n_eval, B, _, H, W = p_steps.shape
+    npx, hw = B * H * W, H * W
+    dev = p_steps.device
+    lib = _lib.load()
+    per = lib.dvd_mlp_save_bytes_per_eval(ctypes.byref(cfg), npx)
+    dy = torch.empty(lib.dvd_mlp_dy_bytes(ctypes.byref(cfg), npx), dtype=torch.uint8, device=dev)
+    a = None
+    gb5 = grad_b[5]
+    if gb5.numel() != 3:
+        raise ValueError('grad of the output bias must have 3 elements')
+    gw_arr, gb_arr = _ptr_array(grad_w), _ptr_array(grad_b)
+    for e in range(n_eval - 1, -1, -1):
+        a_out = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+        gs = g_steps[e] if g_steps is not None else None
+        save_e = ctypes.c_void_p(sv.data_ptr() + e * per)
+        _lib.check(lib.dvd_mlp_dgrad(ctypes.byref(cfg), _ptr(packed.bwd), _ptr(p_steps[e]),
+                                     _ptr(t0) if cfg.time_dependent else ctypes.c_void_p(0), float(dt), e,
+                                     int(e < n_acc and g_acc is not None), _ptr(g_acc), _ptr(gs), _ptr(a), _ptr(a_out),
+                                     save_e, _ptr(dy), _ptr(gb5), npx, hw, _stream()), 'dvd_mlp_dgrad')
+        _lib.check(lib.dvd_mlp_wgrad(ctypes.byref(cfg), save_e, _ptr(dy), gw_arr, gb_arr, npx, _stream()),
+                   'dvd_mlp_wgrad')
+        a = a_out
+    return a
+
+
+def acc_reg(s0, s1, acc_mul, gscale=1.0, want_grad=True):
+    """Model._opt_reg value + gradients w.r.t. (s0, s1) (smf.py:326-344)."""
+    _chk(s0, 's0'), _chk(s1, 's1', s0.shape)
+    lib = _lib.load()
+    g0 = torch.empty_like(s0) if want_grad else None
+    g1 = torch.empty_like(s1) if want_grad else None
+    partials = torch.empty(1024, dtype=torch.float32, device=s0.device)
+    out = torch.empty(1, dtype=torch.float32, device=s0.device)
+    _lib.check(lib.dvd_acc_reg(_ptr(s0), _ptr(s1), float(acc_mul), float(gscale), _ptr(g0), _ptr(g1), _ptr(partials),
+                               _ptr(out), s0.numel(), _stream()), 'dvd_acc_reg')
+    return out, g0, g1
+
+
+class SceneFlowChain(torch.autograd.Function):
+    """Euler chain of the scene-flow field as one autograd node.
+
+    forward(p0, t0, w0..w5, b0..b5 | packed, dt, n_eval, n_acc) -> (acc, s_steps)
+    acc = sum_{i<n_acc} s_i   (Model.forward_sf_net_multi_step, smf.py:360-367);
+    s_steps [n_eval,B,3,H,W] exposes the individual steps (the acceleration regulariser reuses s_0, s_1)."""
+
+    @staticmethod
+    def forward(ctx, p0, t0, packed, dt, n_eval, n_acc, *params):
+        need = any(ctx.needs_input_grad)
+        p0c = p0.contiguous()
+        f = mlp_chain_fwd(packed, p0c, t0, dt, n_eval, n_acc, save=need, want_steps=True)
+        ctx.packed, ctx.dt, ctx.n_acc, ctx.t0 = packed, dt, n_acc, t0
+        ctx.fwd = f
+        ctx.param_shapes = [p.shape for p in params]
+        return f['acc'], f['s_steps']
+
+    @staticmethod
+    def backward(ctx, g_acc, g_steps):
+        f = ctx.fwd
+        n_eval = f['p_steps'].shape[0]
+        dev = f['p_steps'].device
+        shapes = ctx.param_shapes
+        gw = [torch.zeros(shapes[l], dtype=torch.float32, device=dev) for l in range(6)]
+        gb = [torch.zeros(shapes[6 + l], dtype=torch.float32, device=dev) for l in range(6)]
+        g_acc = g_acc.contiguous() if g_acc is not None else None
+        gsl = None
+        if g_steps is not None:
+            g_steps = g_steps.contiguous()
+            gsl = [g_steps[e] for e in range(n_eval)]
+        gp = mlp_chain_bwd(ctx.packed, f, ctx.t0, ctx.dt, ctx.n_acc, g_acc, gsl, gw, gb)
+        ctx.fwd = None
+        return (gp, None, None, None, None, None, *gw, *gb)
+
+
+def scene_flow_chain(p0, t0, packed, dt, n_eval, n_acc, weights, biases):
+    return SceneFlowChain.apply(p0, t0, packed, float(dt), int(n_eval), int(n_acc), *weights, *biases)

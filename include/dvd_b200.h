@@ -94,8 +94,67 @@ int dvd_reproject_materialize(const float* depth_1, const float* depth_2, const 
 int dvd_selftest_umma(const float* A, const float* B, float* D, int K, int N, int mode, int passes,
                       void* stream);
 
-/* ---- scene-flow MLP (M1-M4, L2): networks/blocks.py:19-34, networks/sceneflow_field.py:20-53,
- *      models/scene_flow_motion_field.py:326-367 — declared in the MLP section below ---------- */
+/* ---- scene-flow MLP (M1-M4, L2) ---------------------------------------------------------------
+ * networks/blocks.py:19-34 (PeriodicEmbed), networks/sceneflow_field.py:20-53 (SceneFlowFieldNet:
+ * 1x1 convs n_in->256->256->256->256->256->3, LeakyReLU 0.2), models/scene_flow_motion_field.py:346-367
+ * (forward_sf_net: / sf_mag_div; forward_sf_net_multi_step: Euler chain) and :326-344 (_opt_reg).
+ *
+ * All GEMMs run on tcgen05 tensor cores with fp32 emulated as two bf16 planes (x = hi + lo,
+ * D += Ahi*Bhi + Alo*Bhi + Ahi*Blo, fp32 accumulate in TMEM): error ~2e-5, i.e. tighter than the
+ * TF32 path the reference itself takes on a GPU (cudnn.allow_tf32 default).
+ * Fixed by the reference ctor (smf.py:107): width 256, 4 hidden layers, 3 outputs.             */
+typedef struct dvd_mlp_cfg {
+  int   n_freq_xyz;      /* --n_freq_xyz (16) */
+  int   n_freq_t;        /* --n_freq_t   (16) */
+  int   time_dependent;  /* --time_dependent */
+  float sf_mag_div;      /* --sf_mag_div (100) */
+  float freq_xyz[16];    /* torch.linspace(1, n_freq+1, n_freq) in fp32 (networks/blocks.py:23-24) */
+  float freq_t[16];
+} dvd_mlp_cfg;
+
+/* sizes (bytes) of the caller-allocated scratch buffers for a given configuration */
+size_t dvd_mlp_packed_weights_bytes(const dvd_mlp_cfg* cfg);            /* one image (fwd or bwd) */
+size_t dvd_mlp_save_bytes_per_eval(const dvd_mlp_cfg* cfg, long npx);   /* activations + masks of one eval */
+size_t dvd_mlp_dy_bytes(const dvd_mlp_cfg* cfg, long npx);              /* dY scratch of one eval */
+
+/* fp32 weights -> bf16 (hi,lo) planes in the UMMA shared-memory image (SWIZZLE_128B, K-major blocks),
+ * once per optimiser step. w[l] = convs.{l}.conv.weight [out,in] row-major, l = 0..5 (device ptrs,
+ * host array). packed_fwd feeds the forward chain, packed_bwd (transposed) the dgrad chain.      */
+int dvd_mlp_pack_weights(const dvd_mlp_cfg* cfg, const float* const* w, void* packed_fwd, void* packed_bwd,
+                         void* stream);
+
+/* Euler chain forward (M1-M4): for i < n_eval: s_i = MLP(p_i, t_i)/sf_mag_div; p_{i+1} = p_i + s_i;
+ * t_{i+1} = t_i + dt.  acc = sum_{i<n_acc} s_i.
+ *   p0 [B,3,H,W], t0 [B,1,H,W] (NULL if not time_dependent), npx = B*H*W, hw = H*W
+ *   bias: fp32 [5*256 + 16] = b_0..b_4, b_5 (3 used)
+ *   acc [B,3,H,W] (may be NULL), s_steps [n_eval,B,3,H,W] (may be NULL)
+ *   save (may be NULL = inference): n_eval * dvd_mlp_save_bytes_per_eval(); p_steps [n_eval,B,3,H,W]
+ *   must be non-NULL when save is.                                                              */
+int dvd_mlp_chain_fwd(const dvd_mlp_cfg* cfg, const void* packed_fwd, const float* bias,
+                      const float* p0, const float* t0, float dt, int n_eval, int n_acc,
+                      float* acc, float* s_steps, float* p_steps, void* save,
+                      long npx, long hw, void* stream);
+
+/* backward of ONE eval e of the chain (call for e = n_eval-1 .. 0):
+ *   gs = (e < n_acc ? g_acc : 0) + g_step + a_in      (each [B,3,H,W], any may be NULL)
+ *   a_out = a_in + J_e^T gs                            (a_out may alias a_in)
+ *   writes dY scratch (for dvd_mlp_wgrad) and atomically accumulates g_bias5[3].                */
+int dvd_mlp_dgrad(const dvd_mlp_cfg* cfg, const void* packed_bwd, const float* p_e, const float* t0,
+                  float dt, int e, int use_g_acc, const float* g_acc, const float* g_step,
+                  const float* a_in, float* a_out, const void* save_e, void* dy_scratch,
+                  float* g_bias5, long npx, long hw, void* stream);
+
+/* weight/bias gradients of ONE eval: g_w[l] += dY_l^T X_l, g_b[l] += sum dY_l (l = 0..4), g_w[5]
+ * likewise (g_b[5] is accumulated by dvd_mlp_dgrad). g_w / g_b: host arrays of 6 device pointers
+ * with the layout of w / bias; accumulated with fp32 atomics (zero them once per step).          */
+int dvd_mlp_wgrad(const dvd_mlp_cfg* cfg, const void* save_e, const void* dy_scratch,
+                  float* const* g_w, float* const* g_b, long npx, void* stream);
+
+/* L2  Model._opt_reg (smf.py:326-344) on the chain's own s_0, s_1:
+ *   loss = acc_mul * sum|s1 - s0| / (numel + 1e-6);  g_s0 = -c*sign(s1-s0), g_s1 = +c*sign(s1-s0)
+ *   partials: >= 1024 floats scratch; loss_out: 1 float (device).                                */
+int dvd_acc_reg(const float* s0, const float* s1, float acc_mul, float gscale, float* g_s0, float* g_s1,
+                float* partials, float* loss_out, long numel, void* stream);
 
 #ifdef __cplusplus
 }
