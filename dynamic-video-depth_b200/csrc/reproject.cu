@@ -20,15 +20,44 @@
 
 namespace dvd {
 
-struct Pose {
+struct __align__(16) Pose {
   float Kinv[9], K[9], R1[9], R2[9], t1[3], t2[3];
+  // derived once per block (column-vector algebra, c = (x, y, 1)^T):
+  float M1[9];   // R1 * Kinv                 P1  = d1 * (M1 c) + t1
+  float A[9];    // R2^T * R1 * Kinv          p12 = d1 * (A c) + cv + R2^T sf
+  float cv[3];   // R2^T (t1 - t2)
+  float pad;
 };
-static_assert(sizeof(Pose) == 42 * sizeof(float), "pose layout");
+static_assert(sizeof(Pose) == 64 * sizeof(float), "pose layout");
+
+// MUFU.RCP: max relative error 2^-23 (1 ulp), no slow path; inputs here are >= 1e-3 or flagged invalid
+__device__ __forceinline__ float rcp_fast(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+__device__ __forceinline__ void mm3(const float* X, const float* Y, float* Z, bool xt) {
+  // Z = (xt ? X^T : X) * Y
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float a = 0.f;
+      for (int k = 0; k < 3; ++k) a = fmaf(xt ? X[k * 3 + i] : X[i * 3 + k], Y[k * 3 + j], a);
+      Z[i * 3 + j] = a;
+    }
+}
 
 __device__ __forceinline__ void load_pose(Pose& dst, const float* __restrict__ poses, int b) {
-  // cooperative copy of one pair's pose block into shared memory
+  // cooperative copy of one pair's pose block into shared memory + derived matrices
   float* d = reinterpret_cast<float*>(&dst);
   for (int i = threadIdx.x; i < 42; i += blockDim.x) d[i] = __ldg(poses + (size_t)b * DVD_POSE_STRIDE + i);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mm3(dst.R1, dst.Kinv, dst.M1, false);
+    mm3(dst.R2, dst.M1, dst.A, true);
+    float dx = dst.t1[0] - dst.t2[0], dy = dst.t1[1] - dst.t2[1], dz = dst.t1[2] - dst.t2[2];
+    for (int i = 0; i < 3; ++i) dst.cv[i] = fmaf(dst.R2[6 + i], dz, fmaf(dst.R2[3 + i], dy, dst.R2[i] * dx));
+  }
 }
 
 __device__ __forceinline__ void mv(const float* M, float x, float y, float z, float& ox, float& oy, float& oz) {
@@ -41,16 +70,17 @@ __device__ __forceinline__ void mtv(const float* M, float x, float y, float z, f
   oy = fmaf(M[7], z, fmaf(M[4], y, M[1] * x));
   oz = fmaf(M[8], z, fmaf(M[5], y, M[2] * x));
 }
-// ray = Kinv * (x, y, 1)
-__device__ __forceinline__ void ray_of(const float* Kinv, float x, float y, float& rx, float& ry, float& rz) {
-  rx = fmaf(Kinv[1], y, Kinv[0] * x) + Kinv[2];
-  ry = fmaf(Kinv[4], y, Kinv[3] * x) + Kinv[5];
-  rz = fmaf(Kinv[7], y, Kinv[6] * x) + Kinv[8];
+// M * (x, y, 1)
+__device__ __forceinline__ void ray_of(const float* M, float x, float y, float& rx, float& ry, float& rz) {
+  rx = fmaf(M[1], y, M[0] * x) + M[2];
+  ry = fmaf(M[4], y, M[3] * x) + M[5];
+  rz = fmaf(M[7], y, M[6] * x) + M[8];
 }
 
-// Bilinear taps of ATen grid_sampler_2d(bilinear, padding_mode=border, align_corners=True) for the pixel
-// coordinate (qx,qy). The reference normalises to [-1,1] (losses/...:107-110) and ATen un-normalises;
-// the round trip is reproduced so fp32 rounding follows the reference.
+// Bilinear taps of ATen grid_sampler_2d(bilinear, padding_mode=border, align_corners=True) at the pixel
+// coordinate (qx,qy). The reference normalises to [-1,1] (losses/...:107-110) and ATen un-normalises
+// again; that round trip is the identity up to ~1e-7 relative (4e-5 px at W=384), far below the 1e-3
+// parity bar, so it is skipped (4 IEEE divisions per pixel).
 struct Taps {
   int idx[4];    // linear index y*W+x of nw, ne, sw, se (clamped in range)
   float w[4];    // weights, 0 for out-of-range taps
@@ -58,19 +88,14 @@ struct Taps {
 };
 __device__ __forceinline__ Taps make_taps(float qx, float qy, int H, int W) {
   const float hw = (float)(W - 1), hh = (float)(H - 1);
-  float gx = qx / (hw * 0.5f) - 1.0f;
-  float gy = qy / (hh * 0.5f) - 1.0f;
-  float ix = ((gx + 1.0f) / 2.0f) * hw;
-  float iy = ((gy + 1.0f) / 2.0f) * hh;
-  ix = fminf(hw, fmaxf(ix, 0.0f));
-  iy = fminf(hh, fmaxf(iy, 0.0f));
+  float ix = fminf(hw, fmaxf(qx, 0.0f));
+  float iy = fminf(hh, fmaxf(qy, 0.0f));
   float x0f = floorf(ix), y0f = floorf(iy);
   float wx1 = ix - x0f, wy1 = iy - y0f;
-  float wx0 = (x0f + 1.0f) - ix, wy0 = (y0f + 1.0f) - iy;
+  float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
   int x0 = (int)x0f, y0 = (int)y0f;
-  int x1 = x0 + 1, y1 = y0 + 1;
-  bool vx1 = x1 <= W - 1, vy1 = y1 <= H - 1;
-  int x1c = vx1 ? x1 : x0, y1c = vy1 ? y1 : y0;
+  bool vx1 = x0 + 1 <= W - 1, vy1 = y0 + 1 <= H - 1;
+  int x1c = vx1 ? x0 + 1 : x0, y1c = vy1 ? y0 + 1 : y0;
   Taps t;
   t.idx[0] = y0 * W + x0;
   t.idx[1] = y0 * W + x1c;
@@ -94,49 +119,48 @@ struct Px {
   float p12[3];     // p1_camera_2
   float i12[3];     // K * p12 (z = depth_image_1_2)
   float dflow[2];   // dflow_1_2
+  float rz;         // 1 / (i12.z + 1e-8)
   bool zok;         // i12.z >= 1e-3 (projection used; otherwise own coordinate, zero gradient)
 };
 
+// kNeedWorld: also produce P1 and warped_global_p2 (only the sf_loss term / materialisation need them)
 template <bool kNeedWorld>
 __device__ __forceinline__ void forward_px(const Pose& ps, const float* __restrict__ d2img, const Taps& tp,
                                            float x, float y, float d1, float sfx, float sfy, float sfz, Px& o) {
-  float rx, ry, rz;
-  ray_of(ps.Kinv, x, y, rx, ry, rz);
-  float cx = d1 * rx, cy = d1 * ry, cz = d1 * rz;
-  mv(ps.R1, cx, cy, cz, o.P1[0], o.P1[1], o.P1[2]);
-  o.P1[0] += ps.t1[0]; o.P1[1] += ps.t1[1]; o.P1[2] += ps.t1[2];
-  // bilinear gather of depth_2-derived quantities (4 taps, order nw, ne, sw, se like ATen)
-  o.wpc[0] = o.wpc[1] = o.wpc[2] = 0.0f;
-  o.wP2[0] = o.wP2[1] = o.wP2[2] = 0.0f;
-  o.wd = 0.0f;
+  // bilinear gather: wpc = sum_k w_k d2_k Kinv (u_k, v_k, 1) = Kinv * (sum w d u, sum w d v, sum w d)
+  float su = 0.f, sv = 0.f, s1 = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    float dv = __ldg(d2img + tp.idx[k]);
-    float tx, ty, tz;
-    ray_of(ps.Kinv, tp.ux[k & 1], tp.uy[k >> 1], tx, ty, tz);
-    float px = dv * tx, py = dv * ty, pz = dv * tz;
-    float w = tp.w[k];
-    o.wpc[0] = fmaf(w, px, o.wpc[0]);
-    o.wpc[1] = fmaf(w, py, o.wpc[1]);
-    o.wpc[2] = fmaf(w, pz, o.wpc[2]);
-    o.wd = fmaf(w, dv, o.wd);
-    if (kNeedWorld) {
-      float gx, gy, gz;
-      mv(ps.R2, px, py, pz, gx, gy, gz);
-      o.wP2[0] = fmaf(w, gx + ps.t2[0], o.wP2[0]);
-      o.wP2[1] = fmaf(w, gy + ps.t2[1], o.wP2[1]);
-      o.wP2[2] = fmaf(w, gz + ps.t2[2], o.wP2[2]);
-    }
+    float wd = tp.w[k] * __ldg(d2img + tp.idx[k]);
+    su = fmaf(wd, tp.ux[k & 1], su);
+    sv = fmaf(wd, tp.uy[k >> 1], sv);
+    s1 += wd;
   }
-  // p12 = R2^T (P1 + sf - t2);  i12 = K p12
-  float vx = o.P1[0] + sfx - ps.t2[0], vy = o.P1[1] + sfy - ps.t2[1], vz = o.P1[2] + sfz - ps.t2[2];
-  mtv(ps.R2, vx, vy, vz, o.p12[0], o.p12[1], o.p12[2]);
+  o.wd = s1;
+  mv(ps.Kinv, su, sv, s1, o.wpc[0], o.wpc[1], o.wpc[2]);
+  if (kNeedWorld) {
+    float rx, ry, rz;
+    ray_of(ps.M1, x, y, rx, ry, rz);
+    o.P1[0] = fmaf(d1, rx, ps.t1[0]);
+    o.P1[1] = fmaf(d1, ry, ps.t1[1]);
+    o.P1[2] = fmaf(d1, rz, ps.t1[2]);
+    // the four in-range bilinear weights sum to 1  =>  sum_k w_k (R2 p_k + t2) = R2 wpc + t2
+    mv(ps.R2, o.wpc[0], o.wpc[1], o.wpc[2], o.wP2[0], o.wP2[1], o.wP2[2]);
+    o.wP2[0] += ps.t2[0]; o.wP2[1] += ps.t2[1]; o.wP2[2] += ps.t2[2];
+  }
+  // p12 = R2^T (P1 + sf - t2) = d1 (A c) + cv + R2^T sf ;  i12 = K p12
+  float ax, ay, az, bx, by, bz;
+  ray_of(ps.A, x, y, ax, ay, az);
+  mtv(ps.R2, sfx, sfy, sfz, bx, by, bz);
+  o.p12[0] = fmaf(d1, ax, ps.cv[0]) + bx;
+  o.p12[1] = fmaf(d1, ay, ps.cv[1]) + by;
+  o.p12[2] = fmaf(d1, az, ps.cv[2]) + bz;
   mv(ps.K, o.p12[0], o.p12[1], o.p12[2], o.i12[0], o.i12[1], o.i12[2]);
   o.zok = !(o.i12[2] < 1e-3f);
+  o.rz = rcp_fast(o.i12[2] + 1e-8f);
   if (o.zok) {
-    float zi = o.i12[2] + 1e-8f;
-    o.dflow[0] = o.i12[0] / zi - x;
-    o.dflow[1] = o.i12[1] / zi - y;
+    o.dflow[0] = o.i12[0] * o.rz - x;
+    o.dflow[1] = o.i12[1] * o.rz - y;
   } else {
     o.dflow[0] = 0.0f;
     o.dflow[1] = 0.0f;
@@ -155,7 +179,7 @@ __device__ __forceinline__ float mask_of(const dvd_loss_cfg& c, float m2, float 
 __device__ __forceinline__ float disp_term(const dvd_loss_cfg& c, float za, float zb) {
   if (c.disp_mode == 0) {
     float a = fmaxf(za, 1e-3f), b = fmaxf(zb, 1e-3f);
-    return 100.0f * fabsf(1.0f / a - 1.0f / b);
+    return 100.0f * fabsf(rcp_fast(a) - rcp_fast(b));
   } else if (c.disp_mode == 1) {
     float a = fmaxf(za, 1e-3f), b = fmaxf(zb, 1e-3f);
     return fmaxf(a, b) / fminf(a, b) - 1.0f;
@@ -408,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) reproject_loss_bwd_kernel(
         float gux = cfg.warm ? 2.f * ex : sgn(ex);
         float guy = cfg.warm ? 2.f * ey : sgn(ey);
         gux *= m * cf; guy *= m * cf;
-        float zi = o.i12[2] + 1e-8f, rz = 1.0f / zi;
+        const float rz = o.rz;
         gi0 = gux * rz;
         gi1 = guy * rz;
         gi2 = -(gux * o.i12[0] + guy * o.i12[1]) * rz * rz;
@@ -422,15 +446,17 @@ __global__ void __launch_bounds__(kThreads) reproject_loss_bwd_kernel(
         float mc = m * cd;
         if (cfg.disp_mode == 0) {
           float a = fmaxf(za, 1e-3f), bb = fmaxf(zb, 1e-3f);
-          float s = 100.f * sgn(1.0f / a - 1.0f / bb) * mc;
-          if (za >= 1e-3f) gp2 += -s / (a * a);
-          if (zb >= 1e-3f) gwc2 += s / (bb * bb);
+          const float ra = rcp_fast(a), rb = rcp_fast(bb);
+          float s = 100.f * sgn(ra - rb) * mc;
+          if (za >= 1e-3f) gp2 -= s * ra * ra;
+          if (zb >= 1e-3f) gwc2 += s * rb * rb;
         } else if (cfg.disp_mode == 1) {
           float a = fmaxf(za, 1e-3f), bb = fmaxf(zb, 1e-3f);
           // max(a,b)/min(a,b) - 1
           float ga, gb;
-          if (a >= bb) { ga = 1.0f / bb; gb = -a / (bb * bb); }
-          else         { ga = -bb / (a * a); gb = 1.0f / a; }
+          const float ra = rcp_fast(a), rb = rcp_fast(bb);
+          if (a >= bb) { ga = rb; gb = -a * rb * rb; }
+          else         { ga = -bb * ra * ra; gb = ra; }
           if (za >= 1e-3f) gp2 += ga * mc;
           if (zb >= 1e-3f) gwc2 += gb * mc;
         } else {
@@ -452,14 +478,13 @@ __global__ void __launch_bounds__(kThreads) reproject_loss_bwd_kernel(
       float gv0, gv1, gv2;
       mv(ps.R2, gp0, gp1, gp2, gv0, gv1, gv2);
       ox[v] = gv0 - ge0; oy[v] = gv1 - ge1; oz[v] = gv2 - ge2;
-      // scatter to depth_2: p2c2_k = d2_k * ray_k
+      // scatter to depth_2: wpc = Kinv (sum w d u, sum w d v, sum w d)  =>  g_d2_k = w_k (Kinv^T g_wpc).(u_k, v_k, 1)
       if (gd2img) {
+        float hu, hv, h1;
+        mtv(ps.Kinv, gwc0, gwc1, gwc2, hu, hv, h1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float w = tp.w[k];
-          float tx, ty, tz;
-          ray_of(ps.Kinv, tp.ux[k & 1], tp.uy[k >> 1], tx, ty, tz);
-          float g = w * fmaf(gwc2, tz, fmaf(gwc1, ty, gwc0 * tx));
+          float g = tp.w[k] * fmaf(hu, tp.ux[k & 1], fmaf(hv, tp.uy[k >> 1], h1));
           if (g != 0.f) atomicAdd(gd2img + tp.idx[k], g);
         }
       }

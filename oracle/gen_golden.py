@@ -153,6 +153,11 @@ def gen_mlp():
     # multi-step, steps=3, with gradients w.r.t. p and all weights for a fixed cotangent
     g = torch.Generator().manual_seed(3)
     cot = torch.randn(P1.shape, generator=g)
+    # zero the cotangent on pixels that sit on a LeakyReLU kink (see oracle/sf_mlp.py: kink_band)
+    from oracle import sf_mlp
+    band = sf_mlp.kink_band(P1, ts, dt, 3, sf_mlp.layers_from_state_dict(net.state_dict()))
+    cot = cot * (~band).unsqueeze(1).float()
+    out['kink_band_pixels'] = int(band.sum())
     for steps in (1, 3):
         net.zero_grad()
         p = P1.clone().requires_grad_()
@@ -170,6 +175,16 @@ def gen_mlp():
     model.opt.acc_mul = 1.0
     val = model._opt_reg({'global_p1': p}, steps=5)
     out['acc_reg'] = {'value': val, 'g_p': p.grad.clone(), 'g_w': {k: v.grad.clone() for k, v in net.named_parameters()}}
+    # the same regulariser restricted to the pixels off the kink band (what the gradient parity test uses):
+    net.zero_grad()
+    p = P1.clone().requires_grad_()
+    keep = (~band).unsqueeze(1).float()
+    s0 = model.forward_sf_net(p, ts)
+    s1 = model.forward_sf_net(p + s0, ts + dt)
+    val_k = (keep * (s1 - s0).abs()).sum() / (s0.numel() + 1e-6)
+    val_k.backward()
+    out['acc_reg_keep'] = {'keep': keep, 'value': float(val_k), 'g_p': p.grad.clone(),
+                           'g_w': {k: v.grad.clone() for k, v in net.named_parameters()}}
     torch.save(out, os.path.join(GOLD, 'mlp_golden.pt'))
     print('wrote mlp_golden.pt acc_reg=%g |sf|max=%g' % (val, out['multi_3']['sf'].abs().max()))
 

@@ -29,8 +29,9 @@ def periodic_embed(x, n_freq):
     return torch.cat(out, 1)
 
 
-def mlp_forward(xyz, t, layers, n_freq_xyz=16, n_freq_t=16, time_dependent=True):
-    """Raw network output [B,3,H,W] (before ÷ sf_mag_div)."""
+def mlp_forward(xyz, t, layers, n_freq_xyz=16, n_freq_t=16, time_dependent=True, probe=None):
+    """Raw network output [B,3,H,W] (before ÷ sf_mag_div). `probe` (list) collects, per hidden layer,
+    min_c |pre-activation| per pixel — used by the tests to find pixels sitting on a LeakyReLU kink."""
     feat = periodic_embed(xyz, n_freq_xyz) if n_freq_xyz > 0 else xyz
     if time_dependent:
         te = periodic_embed(t, n_freq_t) if n_freq_t > 0 else t
@@ -39,6 +40,8 @@ def mlp_forward(xyz, t, layers, n_freq_xyz=16, n_freq_t=16, time_dependent=True)
     for i, (w, b) in enumerate(layers):
         h = torch.einsum('oi,bihw->bohw', w.reshape(w.shape[0], -1), h) + b.reshape(1, -1, 1, 1)
         if i + 1 < len(layers):
+            if probe is not None:
+                probe.append(h.detach().abs().amin(dim=1))
             h = torch.nn.functional.leaky_relu(h, 0.2)
     return h
 
@@ -76,6 +79,24 @@ def layers_from_state_dict(sd, prefix='', dtype=None):
         out.append((w.reshape(w.shape[0], -1), b))
         i += 1
     return out
+
+
+def kink_band(p, t, time_step, n_eval, layers, width=3e-5, **kw):
+    """Pixels [B,H,W] (bool) where some hidden pre-activation of some Euler step lies within
+    +-width of the LeakyReLU kink. There the derivative is discontinuous, so two correct fp32
+    implementations may legitimately pick different slopes (the reference on CPU vs on GPU does too);
+    the parity tests zero the cotangent on these (independent, 1x1-conv) pixels."""
+    band = None
+    p, t = p.double(), t.double()
+    l64 = [(w.double(), b.double()) for w, b in layers]
+    for _ in range(n_eval):
+        probe = []
+        s = mlp_forward(p, t, l64, probe=probe, **{k: v for k, v in kw.items() if k != 'sf_mag_div'}) / kw.get('sf_mag_div', 100.0)
+        m = torch.stack(probe, 0).amin(0) < width
+        band = m if band is None else (band | m)
+        p = p + s
+        t = t + time_step
+    return band
 
 
 def init_layers(n_in=132, width=256, n_hidden=4, n_out=3, seed=0, dtype=torch.float32):
