@@ -49,6 +49,7 @@ SIGNATURES = {
     'dvd_mlp_wgrad': [ctypes.POINTER(MlpCfg), _P, _P, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                       ctypes.c_long, _P],
     'dvd_acc_reg': [_P, _P, _F, _F, _P, _P, _P, _P, ctypes.c_long, _P],
+    'dvd_adam_flat': [_P, _P, _P, _P, ctypes.c_long, _F, _F, _F, _F, _I, _F, _P],
 }
 _RESTYPES = {'dvd_last_error': ctypes.c_char_p, 'dvd_mlp_packed_weights_bytes': ctypes.c_size_t,
              'dvd_mlp_save_bytes_per_eval': ctypes.c_size_t, 'dvd_mlp_dy_bytes': ctypes.c_size_t}

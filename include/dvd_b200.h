@@ -156,6 +156,12 @@ int dvd_mlp_wgrad(const dvd_mlp_cfg* cfg, const void* save_e, const void* dy_scr
 int dvd_acc_reg(const float* s0, const float* s1, float acc_mul, float gscale, float* g_s0, float* g_s1,
                 float* partials, float* loss_out, long numel, void* stream);
 
+/* O1  torch.optim.Adam x2 (models/netinterface.py:96-97,127-129; smf.py:113-115,212-213) as one
+ * launch over a flat fp32 buffer: amsgrad=False, weight_decay=0; `step` counts from 1; the
+ * gradient is multiplied by gscale first (1/world_size after a sum all-reduce).                */
+int dvd_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                  float beta2, float eps, int step, float gscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
