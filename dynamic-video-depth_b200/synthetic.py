@@ -104,3 +104,55 @@ def make_depths(B, H, W, seed=1, lo=2.0, hi=8.0, dtype=torch.float32):
     lo_res = torch.rand(B, 1, (H + 15) // 16 + 1, (W + 15) // 16 + 1, generator=g, dtype=torch.float64)
     d = torch.nn.functional.interpolate(lo_res, size=(H, W), mode='bilinear', align_corners=True)
     return (lo + (hi - lo) * d).to(dtype).contiguous()
+
+
+def default_opt(**over):
+    """argparse.Namespace with the flags of experiments/davis/train_sequence.sh:24-63 (the configuration
+    BASELINE.json's metric is quoted on): joint phase needs epoch > warm_sf."""
+    import argparse
+    d = dict(optim='adam', lr=1e-6, adam_beta1=0.5, adam_beta2=0.9, full_logdir=None, global_rank=0,
+             dataset='davis_sequence', batch_size=1, epoch_batches=2000, vis_every_train=0, vis_at_start=True,
+             vis_batches_train=0, multiprocess_distributed=False,
+             l1_mul=0.0, disp_mul=1.0, one_way=True, loss_type='l1', scene_lr_mul=1000.0, n_down=3,
+             weight_steps=False, sf_min_mul=0, sf_quantile=0.5, static=False, static_mul=1, flow_mul=1.0,
+             acc_mul=1.0, si_mul=0, cos_mul=0, motion_seg_hard=False, warm_mul=1, interp_steps=5,
+             warm_static=False, use_disp=True, use_disp_ratio=False, time_dependent=True, use_cnn=False,
+             use_embedding=False, use_motion_seg=False, warm_reg=False, warm_sf=5, n_freq_xyz=16, n_freq_t=16,
+             sf_mag_div=100.0, midas=True)
+    d.update(over)
+    return argparse.Namespace(**d)
+
+
+def seed_net_(net, seed=0, head_bias=None, head_gain=40.0):
+    """Deterministic weights that depend only on parameter NAMES (not on construction order), so the
+    reference net and the dvd_b200 mirror get bit-identical values. Variance-preserving: weights
+    N(0, 1/fan_in); the last BN of every residual branch is damped (x0.25) so that a 101-layer random
+    ResNeXt does not blow up; BN running stats randomised around (0, 1). For MiDaS the 1-channel head
+    gets `head_bias` (depth = 10000/out must land in the valid < 100 range) and its
+    weights `head_gain` x larger so that the synthetic depth map varies spatially (~ +-20 %)."""
+    import hashlib
+    with torch.no_grad():
+        for name, t in list(net.named_parameters()) + list(net.named_buffers()):
+            if not t.dtype.is_floating_point:
+                continue
+            h = int(hashlib.sha1(('%d:%s' % (seed, name)).encode()).hexdigest()[:8], 16)
+            g = torch.Generator().manual_seed(h)
+            leaf = name.split('.')[-1]
+            if leaf == 'running_var':
+                v = 0.75 + 0.5 * torch.rand(t.shape, generator=g)
+            elif leaf == 'running_mean':
+                v = 0.05 * torch.randn(t.shape, generator=g)
+            elif t.dim() >= 2:
+                v = torch.randn(t.shape, generator=g) * math.sqrt(1.0 / t[0].numel())
+            elif leaf == 'weight':   # BN affine scale
+                v = 1.0 + 0.1 * (torch.rand(t.shape, generator=g) - 0.5)
+                if '.bn3.' in name:
+                    v = 0.25 * v
+            else:
+                v = 0.02 * (torch.rand(t.shape, generator=g) - 0.5)
+            t.copy_(v.to(t.dtype))
+        if head_bias is not None:
+            head = net.scratch.output_conv[4]
+            head.weight.mul_(head_gain)
+            head.bias.fill_(head_bias)
+    return net
