@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — frame-pairs/s of the per-video test-time optimisation step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs B] [--impl b200|reference]
+
+One "step" = one joint-phase optimisation step (depth net + scene-flow MLP trainable, flags of
+experiments/davis/train_sequence.sh) over B synthetic frame pairs of 384x224 per GPU (BASELINE.json
+configs[1]: fused re-projection kernels + PyTorch/cuDNN depth net; the scene-flow MLP runs on the tcgen05
+kernels). Gaps cycle through {1,2,4,6,8} step by step (all pairs of one step share the gap).
+Prints ONE JSON line (rank 0). See the repository README / DESIGN.md for the field meanings.
+
+--impl reference : the reference's CPU PyTorch computation, restated by oracle/step.py (kind "port" — the
+Python reference tree cannot travel to the GPU box), on the host cores, one pair per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, N_FRAMES = 224, 384, 80
+GAPS = (1, 2, 4, 6, 8)
+METRIC = 'frame-pairs/sec per step (384x224)'
+UNIT = 'frame-pairs/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--pairs', type=int, default=4, help='frame pairs per step per GPU')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--roofline-pairs', type=int, default=64)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1590.0))), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def step_pairs(step, rank, world, B):
+    """Pairs of one step on one rank: all share the gap (uniform Euler-step count across ranks), disjoint
+    frame ids across ranks — the DistributedSampler-style partition of the pair list (train.py:301-305)."""
+    gap = GAPS[step % len(GAPS)]
+    out = []
+    for j in range(B):
+        f = (step * 7 + (rank * B + j) * 3) % (N_FRAMES - 1 - gap)
+        out.append((f, f + gap))
+    return gap, out
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_steps(n_steps, warmup, quiet=True):
+    """The reference's CPU path (oracle port): joint-phase step, 1 pair, gap 2, 384x224, all host cores."""
+    import torch
+    from dvd_b200 import synthetic
+    from dvd_b200.networks.sceneflow_field import SceneFlowFieldNet
+    from dvd_b200.third_party.MiDaS import MidasNet
+    from oracle import step as ostep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    opt = synthetic.default_opt()
+    depth = synthetic.seed_net_(MidasNet(non_negative=True, normalize_input=True), 0, 2000.0).state_dict()
+    mlp = synthetic.seed_net_(SceneFlowFieldNet(net_width=256, n_layers=4, time_dependent=True, N_freq_xyz=16, N_freq_t=16), 1).state_dict()
+    ad, am = {}, {}
+    times = []
+    for i in range(warmup + n_steps):
+        batch = synthetic.make_batch([(10 + i, 12 + i)], H=H, W=W, n_frames=N_FRAMES, seed=i, leading_dim=False)
+        t0 = time.perf_counter()
+        log, depth, mlp, _ = ostep.train_step(depth, mlp, batch, opt, epoch=6, adam_depth=ad, adam_mlp=am)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {'value': len(times) / total, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d joint-phase step(s) x 1 pair (gap 2) at %dx%d, oracle/step.py on torch CPU, %d threads, %d warm-up'
+                      % (len(times), W, H, torch.get_num_threads(), warmup),
+            'seconds': total, 'last_loss': log['loss']}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb = cpu_reference_steps(args.steps, args.warmup)
+    line = {'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * cb['seconds'] / max(args.steps, 1), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': "synthetic 80-frame sequence, 384x224 (BASELINE.json configs[0]/[1]), joint phase, "
+                                   "1 pair per step, CPU PyTorch path of the reference restated by oracle/step.py"},
+            'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def roofline_reproject(pairs, hbm_peak, peak_kind):
+    """Fused re-projection kernels on a batch >> L2 (pairs x 344 KB x 8 tensors), L2 flushed between launches,
+    CUDA events on the launching (current) stream."""
+    import torch
+    from dvd_b200 import ops, synthetic
+    dev = torch.device('cuda', torch.cuda.current_device())
+    one = synthetic.make_batch([(4, 8)], H=H, W=W, seed=0, leading_dim=False)
+    rep = lambda t: t.to(dev).repeat(pairs, *([1] * (t.dim() - 1))).contiguous()  # noqa: E731
+    flow, mask = rep(one['flow_1_2']), rep(one['mask_2'].reshape(1, H, W))
+    poses = rep(ops.pack_poses_from_batch({k: v for k, v in one.items() if torch.is_tensor(v)}))
+    d1, d2 = rep(synthetic.make_depths(1, H, W, seed=1)), rep(synthetic.make_depths(1, H, W, seed=2))
+    sf = torch.randn(pairs, 3, H, W, device=dev) * 0.05
+    cfg = ops.make_loss_cfg()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    px = pairs * H * W
+    scal = ops.reproject_loss_fwd(d1, d2, flow, mask, sf, poses, cfg)
+    P = ops.unproject_fwd(d1, poses, 1)
+    cases = [('unproject_fwd_kernel', lambda: ops.unproject_fwd(d1, poses, 1), 16),
+             ('reproject_loss_fwd_kernel', lambda: ops.reproject_loss_fwd(d1, d2, flow, mask, sf, poses, cfg), 32),
+             ('reproject_loss_bwd_kernel', lambda: ops.reproject_loss_bwd(d1, d2, flow, mask, sf, poses, cfg, scal), 48),
+             ('unproject_bwd_kernel', lambda: ops.unproject_bwd(P, poses, 1), 16)]
+    out = []
+    for name, fn, bpp in cases:
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        t = sum(ts) / len(ts)
+        out.append({'kernel': name, 'bytes_per_px': bpp, 'us': t * 1e6, 'achieved': px * bpp / t / 1e9,
+                    'frac': px * bpp / t / 1e9 / hbm_peak})
+    tot_t = sum(k['us'] for k in out) * 1e-6
+    dom = max(out[1:3], key=lambda k: k['us'])
+    return {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['achieved'], 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': dom['frac'], 'traffic': None, 'peak_kind': peak_kind,
+            'how': 'CUDA events in bench.py, %d pairs per launch (%.0f MB algorithmic traffic), 256 MB L2 flush between launches'
+                   % (pairs, px * dom['bytes_per_px'] / 1e6),
+            'chain_112B_per_px': {'achieved': px * 112 / tot_t / 1e9, 'frac': px * 112 / tot_t / 1e9 / hbm_peak},
+            'kernels': out}
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --impl b200 needs a GPU: dvd_b200 has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    from dvd_b200 import ops, synthetic
+    from dvd_b200.models import get_model
+    torch.backends.cudnn.allow_tf32 = True         # the reference's own GPU default (torch): TF32 convolutions
+    torch.backends.cudnn.benchmark = True
+    opt = synthetic.default_opt(batch_size=1, multiprocess_distributed=world > 1, global_rank=rank)
+    model = get_model('scene_flow_motion_field')(opt, None)
+    synthetic.seed_net_(model.net_depth, 0, 2000.0)
+    synthetic.seed_net_(model.net_sceneflow, 1)
+    model.to(dev)
+    if world > 1:
+        model.sync_parameters(0)
+    B, K, Wm = args.pairs, args.steps, args.warmup
+    EPOCH = opt.warm_sf + 1   # joint phase
+
+    def host_batch(step):
+        gap, pairs = step_pairs(step, rank, world, B)
+        b = synthetic.make_batch(pairs, H=H, W=W, n_frames=N_FRAMES, seed=1000 * rank + step)
+        return {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+
+    total_steps = Wm + K
+    host = [host_batch(s) for s in range(total_steps)]
+    resident = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host]
+    for rb, hb in zip(resident, host):   # keep the scalar metadata readable on the host without a sync
+        rb['time_step'] = hb['time_step']
+        rb['steps_hint'] = int(round(float(hb['frame_id_2'].reshape(-1)[0] - hb['frame_id_1'].reshape(-1)[0])))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, sampler=None):
+        for s in range(Wm):
+            model._train_on_batch(EPOCH, s, batches[s])
+        barrier()
+        if sampler:
+            sampler.start()
+        ops.LAUNCHES['n'] = 0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        logs = [model._train_on_batch(EPOCH, Wm + s, batches[Wm + s]) for s in range(K)]
+        b.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        t = a.elapsed_time(b) * 1e-3
+        if world > 1:
+            tt = torch.tensor([t], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt)
+        return t, logs, clocks, ops.LAUNCHES['n']
+
+    # (1) device-resident inputs: the headline `value`
+    t_dev, logs, clocks, launches = timed(resident, ClockSampler(local))
+    # (2) end to end through the plug-in call with HOST (pinned) batches: H2D + D2H inside the timed region
+    t_e2e, logs2, _, _ = timed(host)
+    h2d = sum(v.numel() * v.element_size() for v in host[Wm].values() if torch.is_tensor(v))
+    d2h = 9 * 4
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm_peak, tflops_peak, peak_kind = measured_peaks()
+    roof = roofline_reproject(args.roofline_pairs, hbm_peak, peak_kind)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_steps(2, 0)
+    pairs_total = K * B * world
+    line = {
+        'metric': METRIC, 'value': pairs_total / t_dev, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        'ms_per_step': 1e3 * t_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 storage; MLP GEMMs bf16x3-split on tcgen05 (fp32-grade, err ~2e-5); re-projection fp32; depth-net convs cuDNN TF32 (torch default, = reference on GPU)',
+        'data': 'synthetic',
+        'config': {'workload': "synthetic 80-frame sequence 384x224 (BASELINE.json configs[1]: DAVIS 'dog' shape, fused "
+                               "re-projection kernels + PyTorch/cuDNN MiDaS depth net + tcgen05 scene-flow MLP), joint phase "
+                               "(--midas --use_disp --time_dependent --acc_mul 1), gaps cycle 1,2,4,6,8",
+                   'pairs_per_step_per_gpu': B, 'global_pairs_per_step': B * world, 'parallelism': 'dp%d' % world,
+                   'l2': 'per-step working set (depth-net activations + %.1f GB saved MLP activations) >> 126 MB L2; no explicit flush' % (
+                       B * 4.4 * 0.504)},
+        'clocks': clocks,
+        'e2e': {'value': pairs_total / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': 1e3 * t_e2e / K, 'api': 'Model._train_on_batch(epoch, i, pinned-host batch dict)'},
+        'gpu_launches': launches,
+        'roofline': roof,
+        'cpu_baseline': cpu,
+        'last_batch_log': {k: v for k, v in logs[-1].items() if isinstance(v, (int, float))},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == '__main__':
+    main()

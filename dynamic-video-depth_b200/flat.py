@@ -77,6 +77,8 @@ class FlatAdam:
             lib = _lib.load()
             P = ctypes.c_void_p
             st = P(torch.cuda.current_stream().cuda_stream)
+            from . import ops
+            ops.LAUNCHES['n'] += 1
             _lib.check(lib.dvd_adam_flat(P(f.data.data_ptr()), P(f.grad.data_ptr()), P(self.exp_avg.data_ptr()),
                                          P(self.exp_avg_sq.data_ptr()), f.numel, self.lr, self.betas[0], self.betas[1],
                                          self.eps, self.step_count, float(gscale), st), 'dvd_adam_flat')

@@ -191,6 +191,8 @@ class Model(NetInterface):
         is moved to the device so that no host sync is needed."""
         ts1, ts2, dt = batch['time_stamp_1'], batch['time_stamp_2'], batch['time_step']
         dt = float(dt.reshape(-1)[0]) if torch.is_tensor(dt) else float(dt)
+        if 'steps_hint' in batch:   # GPU-resident batches carry the gap so that no device read-back is needed
+            return int(batch['steps_hint']), dt
         gap = float((ts2.reshape(ts2.shape[0], -1)[:, 0] - ts1.reshape(ts1.shape[0], -1)[:, 0]).float().mean())
         return int(round(gap / dt)), dt
 

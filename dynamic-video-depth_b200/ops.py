@@ -12,6 +12,10 @@ from . import _lib
 from ._lib import LossCfg
 
 
+# number of dvd_b200 kernel launches issued through this module (bench.py reports it as gpu_launches)
+LAUNCHES = {'n': 0}
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -71,6 +75,7 @@ def unproject_fwd(depth, poses, which=1):
     _chk(depth, 'depth', (B, 1, H, W)), _chk(poses, 'poses', (B, 48))
     P = torch.empty(B, 3, H, W, dtype=torch.float32, device=depth.device)
     lib = _lib.load()
+    LAUNCHES['n'] += 1
     _lib.check(lib.dvd_unproject_fwd(_ptr(depth), _ptr(poses), _ptr(P), B, H, W, int(which), _stream()),
                'dvd_unproject_fwd')
     return P
@@ -81,6 +86,7 @@ def unproject_bwd(gP, poses, which=1):
     _chk(gP, 'gP', (B, 3, H, W)), _chk(poses, 'poses', (B, 48))
     gd = torch.empty(B, 1, H, W, dtype=torch.float32, device=gP.device)
     lib = _lib.load()
+    LAUNCHES['n'] += 1
     _lib.check(lib.dvd_unproject_bwd(_ptr(gP), _ptr(poses), _ptr(gd), B, H, W, int(which), _stream()),
                'dvd_unproject_bwd')
     return gd
@@ -108,6 +114,7 @@ def reproject_loss_fwd(depth_1, depth_2, flow, mask, sf, poses, cfg):
     n = lib.dvd_reproject_partials_size(B, H, W)
     partials = torch.empty(n, dtype=torch.float32, device=depth_1.device)
     scalars = torch.empty(8, dtype=torch.float32, device=depth_1.device)
+    LAUNCHES['n'] += 2
     _lib.check(lib.dvd_reproject_loss_fwd(_ptr(depth_1), _ptr(depth_2), _ptr(flow), _ptr(mask), _ptr(sf), _ptr(poses),
                                           ctypes.byref(cfg), _ptr(partials), _ptr(scalars), B, H, W, _stream()),
                'dvd_reproject_loss_fwd')
@@ -121,6 +128,7 @@ def reproject_loss_bwd(depth_1, depth_2, flow, mask, sf, poses, cfg, scalars, gs
     g_sf = torch.empty_like(sf)
     g_d2 = torch.empty_like(depth_2) if need_depth_grad else None
     lib = _lib.load()
+    LAUNCHES['n'] += 1
     _lib.check(lib.dvd_reproject_loss_bwd(_ptr(depth_1), _ptr(depth_2), _ptr(flow), _ptr(mask), _ptr(sf), _ptr(poses),
                                           ctypes.byref(cfg), _ptr(scalars), float(gscale), _ptr(gscale_dev),
                                           _ptr(g_sf), _ptr(g_d2), B, H, W, _stream()),
@@ -144,6 +152,7 @@ def reproject_materialize(depth_1, depth_2, flow, sf, poses, keys=None):
             c = 3 if k in _MAT_KEYS3 else (2 if k in _MAT_KEYS2 else 1)
             out[k] = torch.empty(B, c, H, W, dtype=torch.float32, device=depth_1.device)
     lib = _lib.load()
+    LAUNCHES['n'] += 1
     _lib.check(lib.dvd_reproject_materialize(_ptr(depth_1), _ptr(depth_2), _ptr(flow), _ptr(sf), _ptr(poses),
                                              *[_ptr(out.get(k)) for k in allk], B, H, W, _stream()),
                'dvd_reproject_materialize')
@@ -249,6 +258,7 @@ class PackedMlp:
             raise ValueError('the scene-flow MLP has 6 layers')
         ws = [_chk(w.detach(), 'weight[%d]' % i) for i, w in enumerate(weights)]
         lib = _lib.load()
+        LAUNCHES['n'] += 1
         _lib.check(lib.dvd_mlp_pack_weights(ctypes.byref(self.cfg), _ptr_array(ws), _ptr(self.fwd), _ptr(self.bwd),
                                             _stream()), 'dvd_mlp_pack_weights')
         with torch.no_grad():
@@ -275,6 +285,7 @@ def mlp_chain_fwd(packed, p0, t0, dt, n_eval, n_acc, save=False, want_steps=True
         p_steps = torch.empty(n_eval, B, 3, H, W, dtype=torch.float32, device=dev)
         per = lib.dvd_mlp_save_bytes_per_eval(ctypes.byref(cfg), npx)
         sv = torch.empty(n_eval * per, dtype=torch.uint8, device=dev)
+    LAUNCHES['n'] += 1
     _lib.check(lib.dvd_mlp_chain_fwd(ctypes.byref(cfg), _ptr(packed.fwd), _ptr(packed.bias), _ptr(p0),
                                      _ptr(t0) if cfg.time_dependent else ctypes.c_void_p(0), float(dt), int(n_eval),
                                      int(n_acc), _ptr(acc), _ptr(s_steps), _ptr(p_steps), _ptr(sv), npx, hw, _stream()),
@@ -303,10 +314,12 @@ def mlp_chain_bwd(packed, fwd, t0, dt, n_acc, g_acc, g_steps, grad_w, grad_b):
         a_out = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
         gs = g_steps[e] if g_steps is not None else None
         save_e = ctypes.c_void_p(sv.data_ptr() + e * per)
+        LAUNCHES['n'] += 1
         _lib.check(lib.dvd_mlp_dgrad(ctypes.byref(cfg), _ptr(packed.bwd), _ptr(p_steps[e]),
                                      _ptr(t0) if cfg.time_dependent else ctypes.c_void_p(0), float(dt), e,
                                      int(e < n_acc and g_acc is not None), _ptr(g_acc), _ptr(gs), _ptr(a), _ptr(a_out),
                                      save_e, _ptr(dy), _ptr(gb5), npx, hw, _stream()), 'dvd_mlp_dgrad')
+        LAUNCHES['n'] += 1
         _lib.check(lib.dvd_mlp_wgrad(ctypes.byref(cfg), save_e, _ptr(dy), gw_arr, gb_arr, npx, _stream()),
                    'dvd_mlp_wgrad')
         a = a_out
@@ -321,6 +334,7 @@ def acc_reg(s0, s1, acc_mul, gscale=1.0, want_grad=True):
     g1 = torch.empty_like(s1) if want_grad else None
     partials = torch.empty(1024, dtype=torch.float32, device=s0.device)
     out = torch.empty(1, dtype=torch.float32, device=s0.device)
+    LAUNCHES['n'] += 2
     _lib.check(lib.dvd_acc_reg(_ptr(s0), _ptr(s1), float(acc_mul), float(gscale), _ptr(g0), _ptr(g1), _ptr(partials),
                                _ptr(out), s0.numel(), _stream()), 'dvd_acc_reg')
     return out, g0, g1

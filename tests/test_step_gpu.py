@@ -39,6 +39,7 @@ def test_train_step_matches_reference_fixture(step_golden, phase):
     model = make_model(meta)
     batch = synthetic.make_batch(meta['pairs'], H=meta['H'], W=meta['W'], seed=meta['batch_seed'], smooth_flow=True,
                                  flow_sigma=2.0)
+    model.net_depth.eval()   # BN is in eval mode on this path (smf.py:157,168)
     with torch.no_grad():
         d1 = model.net_depth(batch['img_1'][0].cuda())
     assert rel_err(d1, g['depth_1']) < 1e-3
