@@ -6,7 +6,9 @@
 // loaded with ONE 1-D bulk async copy (no tensor map) and consumed by tcgen05.mma directly.
 //   weights fwd  (B operand of Y = X W^T):      rows = out channel, K = in channel
 //   weights bwd  (B operand of dX = dY W):      rows = in channel,  K = out channel
-//   X_l / dY_l   (operands of dW = dY^T X):     rows = channel,     K = pixel (64 pixels per block)
+//   X_l / dY_l   (operands of dW = dY^T X):     MN-major blocks: K = pixel (64 per block), channels
+//                contiguous — each pixel's 64-channel group is one 128-byte row, so the epilogue thread
+//                that owns the pixel writes whole 16-byte chunks (mn128_offset in tc_common.cuh)
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -39,6 +41,8 @@ __host__ __device__ inline int nkc_f(const MlpLayout& L, int l) { return l == 0 
 __host__ __device__ inline int nkc_b(int l) { return l == 5 ? 1 : 4; }
 __host__ __device__ inline int rows_x(const MlpLayout& L, int l) { return l == 0 ? L.kpad0 : kWidth; }
 __host__ __device__ inline int rows_dy(int l) { return l == 5 ? 16 : kWidth; }
+// bytes of one 64-pixel block of an activation / dY array with `rows` channels (64-channel atoms of 8 KB)
+__host__ __device__ inline uint32_t blk_bytes(int rows) { return (uint32_t)((rows + 63) / 64) * 8192u; }
 __host__ __device__ inline int layer_in(const MlpLayout& L, int l) { return l == 0 ? L.nin : kWidth; }
 __host__ __device__ inline int layer_out(int l) { return l == 5 ? 3 : kWidth; }
 
@@ -65,7 +69,7 @@ inline MlpLayout make_layout(const dvd_mlp_cfg& c, long npx) {
   o = 0;
   for (int l = 0; l < kLayers; ++l) {
     L.xs_off[l] = o;
-    o += (size_t)2 * L.nq * rows_x(L, l) * 128;
+    o += (size_t)2 * L.nq * blk_bytes(rows_x(L, l));
   }
   L.mask_off = o;
   o += (size_t)5 * L.ntiles * kTileM * 32;  // 5 layers x 256 bits per pixel
@@ -73,7 +77,7 @@ inline MlpLayout make_layout(const dvd_mlp_cfg& c, long npx) {
   o = 0;
   for (int l = 0; l < kLayers; ++l) {
     L.dy_off[l] = o;
-    o += (size_t)2 * L.nq * rows_dy(l) * 128;
+    o += (size_t)2 * L.nq * blk_bytes(rows_dy(l));
   }
   L.dy_total = (o + 255) & ~(size_t)255;
   return L;

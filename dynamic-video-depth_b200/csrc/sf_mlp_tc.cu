@@ -275,8 +275,8 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
         {
           E emb;
           emb.compute(P.cfg, t, px, py, pz);
-          uint8_t* x0_hi = SAVE ? save_e + L.xs_off[0] + (size_t)chunk * E::KPAD * 128 : nullptr;
-          uint8_t* x0_lo = SAVE ? x0_hi + (size_t)L.nq * E::KPAD * 128 : nullptr;
+          uint8_t* x0_hi = SAVE ? save_e + L.xs_off[0] + (size_t)chunk * blk_bytes(E::KPAD) : nullptr;
+          uint8_t* x0_lo = SAVE ? x0_hi + (size_t)L.nq * blk_bytes(E::KPAD) : nullptr;
 #pragma unroll
           for (int w0 = 0; w0 < E::KPAD / 2; w0 += 8) {
             uint32_t hi[8], lo[8];
@@ -284,15 +284,12 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
             for (int j = 0; j < 8; ++j) split2(emb.get(2 * (w0 + j)), emb.get(2 * (w0 + j) + 1), hi[j], lo[j]);
             tmem_st8(tAhi + w0, hi);
             tmem_st8(tAlo + w0, lo);
-            if (SAVE) {
+            if (SAVE) {   // 16 channels = two 16-byte chunks of this pixel's row
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint32_t n0 = 2 * (w0 + j);
-                const uint32_t o0 = sw128_offset(n0, kq), o1 = sw128_offset(n0 + 1, kq);
-                *reinterpret_cast<uint16_t*>(x0_hi + o0) = (uint16_t)(hi[j] & 0xffffu);
-                *reinterpret_cast<uint16_t*>(x0_hi + o1) = (uint16_t)(hi[j] >> 16);
-                *reinterpret_cast<uint16_t*>(x0_lo + o0) = (uint16_t)(lo[j] & 0xffffu);
-                *reinterpret_cast<uint16_t*>(x0_lo + o1) = (uint16_t)(lo[j] >> 16);
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t o = mn128_offset(2 * w0 + 8 * h, kq);
+                st_global_v4(x0_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+                st_global_v4(x0_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
               }
             }
           }
@@ -306,8 +303,8 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
           d_phase ^= 1u;
           tc_fence_after();
           const float* bl = S.bias + l * 256;
-          uint8_t* x_hi = SAVE ? save_e + L.xs_off[l + 1] + (size_t)chunk * kWidth * 128 : nullptr;
-          uint8_t* x_lo = SAVE ? x_hi + (size_t)L.nq * kWidth * 128 : nullptr;
+          uint8_t* x_hi = SAVE ? save_e + L.xs_off[l + 1] + (size_t)chunk * blk_bytes(kWidth) : nullptr;
+          uint8_t* x_lo = SAVE ? x_hi + (size_t)L.nq * blk_bytes(kWidth) : nullptr;
           uint32_t maskw[8];
 #pragma unroll
           for (int cb = 0; cb < 8; ++cb) {
@@ -329,15 +326,12 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
             maskw[cb] = mb;
             tmem_st16(tAhi + c0 / 2, hi);
             tmem_st16(tAlo + c0 / 2, lo);
-            if (SAVE) {
+            if (SAVE) {   // 32 channels = four 16-byte chunks of this pixel's 128-byte rows
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const uint32_t n0 = c0 + 2 * j;
-                const uint32_t o0 = sw128_offset(n0, kq), o1 = sw128_offset(n0 + 1, kq);
-                *reinterpret_cast<uint16_t*>(x_hi + o0) = (uint16_t)(hi[j] & 0xffffu);
-                *reinterpret_cast<uint16_t*>(x_hi + o1) = (uint16_t)(hi[j] >> 16);
-                *reinterpret_cast<uint16_t*>(x_lo + o0) = (uint16_t)(lo[j] & 0xffffu);
-                *reinterpret_cast<uint16_t*>(x_lo + o1) = (uint16_t)(lo[j] >> 16);
+              for (int h = 0; h < 4; ++h) {
+                const uint32_t o = mn128_offset(c0 + 8 * h, kq);
+                st_global_v4(x_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+                st_global_v4(x_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
               }
             }
           }
@@ -510,15 +504,13 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
         split2(d5z, 0.f, hi[1], lo[1]);
         tmem_st8(tAhi, hi);
         tmem_st8(tAlo, lo);
-        uint8_t* y_hi = P.dy + L.dy_off[5] + (size_t)chunk * 16 * 128;
-        uint8_t* y_lo = y_hi + (size_t)L.nq * 16 * 128;
+        uint8_t* y_hi = P.dy + L.dy_off[5] + (size_t)chunk * blk_bytes(16);
+        uint8_t* y_lo = y_hi + (size_t)L.nq * blk_bytes(16);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t o0 = sw128_offset(2 * j, kq), o1 = sw128_offset(2 * j + 1, kq);
-          *reinterpret_cast<uint16_t*>(y_hi + o0) = (uint16_t)(hi[j] & 0xffffu);
-          *reinterpret_cast<uint16_t*>(y_hi + o1) = (uint16_t)(hi[j] >> 16);
-          *reinterpret_cast<uint16_t*>(y_lo + o0) = (uint16_t)(lo[j] & 0xffffu);
-          *reinterpret_cast<uint16_t*>(y_lo + o1) = (uint16_t)(lo[j] >> 16);
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t o = mn128_offset(8 * h, kq);
+          st_global_v4(y_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+          st_global_v4(y_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
         }
       }
       tmem_st_wait();
@@ -533,8 +525,8 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
                                                          (((size_t)(l - 1) * L.ntiles + tile) * kTileM + row) * 32);
         const uint4 m0 = mp[0], m1 = mp[1];
         const uint32_t maskw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        uint8_t* y_hi = P.dy + L.dy_off[l - 1] + (size_t)chunk * kWidth * 128;
-        uint8_t* y_lo = y_hi + (size_t)L.nq * kWidth * 128;
+        uint8_t* y_hi = P.dy + L.dy_off[l - 1] + (size_t)chunk * blk_bytes(kWidth);
+        uint8_t* y_lo = y_hi + (size_t)L.nq * blk_bytes(kWidth);
 #pragma unroll
         for (int cb = 0; cb < 8; ++cb) {
           const int c0 = cb * 32;
@@ -553,13 +545,10 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
           tmem_st16(tAhi + c0 / 2, hi);
           tmem_st16(tAlo + c0 / 2, lo);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const uint32_t n0 = c0 + 2 * j;
-            const uint32_t o0 = sw128_offset(n0, kq), o1 = sw128_offset(n0 + 1, kq);
-            *reinterpret_cast<uint16_t*>(y_hi + o0) = (uint16_t)(hi[j] & 0xffffu);
-            *reinterpret_cast<uint16_t*>(y_hi + o1) = (uint16_t)(hi[j] >> 16);
-            *reinterpret_cast<uint16_t*>(y_lo + o0) = (uint16_t)(lo[j] & 0xffffu);
-            *reinterpret_cast<uint16_t*>(y_lo + o1) = (uint16_t)(lo[j] >> 16);
+          for (int h = 0; h < 4; ++h) {
+            const uint32_t o = mn128_offset(c0 + 8 * h, kq);
+            st_global_v4(y_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
+            st_global_v4(y_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
           }
         }
         tmem_st_wait();
@@ -627,7 +616,8 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
 }
 
 // =============================================================================================
-// wgrad: D[128, n] += A_blk[128 x 64px] * B_blk[n x 64px]^T over a range of pixel chunks (SS mode)
+// wgrad: D[128, n] += A_blk[128 ch x 64 px] * B_blk[n ch x 64 px]^T over a range of pixel chunks
+// (SS mode, both operands MN-major: channels contiguous, K = pixels)
 struct WgradJob {
   const uint8_t* a_hi;
   const uint8_t* a_lo;
@@ -644,7 +634,7 @@ struct WgradParams {
 };
 constexpr int kWgStages = 2;
 constexpr uint32_t kWgStageBytes = 2 * 16384 + 2 * 32768;
-constexpr size_t kWgradSmemBytes = 1024 + (size_t)kWgStages * kWgStageBytes + 2048 + 256;
+constexpr size_t kWgradSmemBytes = 1024 + (size_t)kWgStages * kWgStageBytes + 8192 + 256;
 
 __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_wgrad_kernel(const __grid_constant__ WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -652,7 +642,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_wgrad_kernel(const __grid_
   uint8_t* stage[kWgStages];
   for (int i = 0; i < kWgStages; ++i) stage[i] = base + (size_t)i * kWgStageBytes;
   uint8_t* ones = base + (size_t)kWgStages * kWgStageBytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ones + 2048);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ones + 8192);
   uint64_t* empty = full + kWgStages;
   uint64_t* done = empty + kWgStages;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(done + 1);
@@ -668,9 +658,10 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_wgrad_kernel(const __grid_
     mbar_init(done, 1);
     fence_mbar_init();
   }
-  // "ones" operand (row 0 = 1.0 bf16, rows 1..15 = 0) for the bias column sums
-  for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(ones)[i] = (i < 32) ? 0x3F803F80u : 0u;
+  // "ones" operand [16 ch x 64 px], MN-major: channel 0 = 1.0 (bf16), channels 1..15 = 0 -> bias column sums
+  for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x < 64) *reinterpret_cast<uint16_t*>(ones + mn128_offset(0, threadIdx.x)) = (uint16_t)0x3F80u;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -681,7 +672,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_wgrad_kernel(const __grid_
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      const uint32_t a_bytes = 16384, b_bytes = (uint32_t)J.n * 128u;
+      const uint32_t a_bytes = 16384, b_bytes = blk_bytes(J.n);
       for (long qq = q0; qq < q1; ++qq, ++it) {
         const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
@@ -696,21 +687,21 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_wgrad_kernel(const __grid_
   } else if (warp == 1) {
     if (lane == 0 && have_work) {
       uint32_t it = 0, accum = 0;
-      const uint32_t idesc = make_idesc_bf16(128, J.n), idesc_b = make_idesc_bf16(128, 16);
+      const uint32_t idesc = make_idesc_bf16(128, J.n, true, true), idesc_b = make_idesc_bf16(128, 16, true, true);
       const uint32_t so = smem_u32(ones);
       for (long qq = q0; qq < q1; ++qq, ++it) {
         const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t sa_hi = smem_u32(stage[s]), sa_lo = sa_hi + 16384, sb_hi = sa_hi + 32768, sb_lo = sa_hi + 65536;
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t ah = make_sdesc_k_sw128(sa_hi + ks * 32), al = make_sdesc_k_sw128(sa_lo + ks * 32);
-          const uint64_t bh = make_sdesc_k_sw128(sb_hi + ks * 32), bl = make_sdesc_k_sw128(sb_lo + ks * 32);
+        for (int ks = 0; ks < 4; ++ks) {   // 16 pixels (K rows of 128 B) per MMA
+          const uint64_t ah = make_sdesc_mn_sw128(sa_hi + ks * 2048, 8192), al = make_sdesc_mn_sw128(sa_lo + ks * 2048, 8192);
+          const uint64_t bh = make_sdesc_mn_sw128(sb_hi + ks * 2048, 8192), bl = make_sdesc_mn_sw128(sb_lo + ks * 2048, 8192);
           umma_ss(tmem + 0, ah, bh, idesc, accum);
           umma_ss(tmem + 0, al, bh, idesc, 1);
           umma_ss(tmem + 0, ah, bl, idesc, 1);
           if (J.bias_out) {
-            const uint64_t od = make_sdesc_k_sw128(so + ks * 32);
+            const uint64_t od = make_sdesc_mn_sw128(so + ks * 2048, 8192);
             umma_ss(tmem + 256, ah, od, idesc_b, accum);
             umma_ss(tmem + 256, al, od, idesc_b, 1);
           }
@@ -927,18 +918,18 @@ extern "C" int dvd_mlp_wgrad(const dvd_mlp_cfg* cfg, const void* save_e, const v
   int nj = 0;
   for (int l = 0; l < kLayers; ++l) {
     DVD_ARG_CHECK(g_w[l] != nullptr, "null g_w[%d]", l);
-    const size_t x_plane = (size_t)L.nq * rows_x(L, l) * 128, y_plane = (size_t)L.nq * rows_dy(l) * 128;
+    const size_t x_plane = (size_t)L.nq * blk_bytes(rows_x(L, l)), y_plane = (size_t)L.nq * blk_bytes(rows_dy(l));
     for (int mh = 0; mh < 2; ++mh) {
       WgradJob& J = P.job[nj++];
       if (l < 5) {
         DVD_ARG_CHECK(g_b[l] != nullptr, "null g_b[%d]", l);
-        J.a_hi = dy + L.dy_off[l]; J.a_lo = J.a_hi + y_plane; J.a_blk = kWidth * 128; J.a_row_off = mh * 128 * 128;
-        J.b_hi = sv + L.xs_off[l]; J.b_lo = J.b_hi + x_plane; J.b_blk = rows_x(L, l) * 128; J.n = rows_x(L, l);
+        J.a_hi = dy + L.dy_off[l]; J.a_lo = J.a_hi + y_plane; J.a_blk = blk_bytes(kWidth); J.a_row_off = mh * 2 * 8192;
+        J.b_hi = sv + L.xs_off[l]; J.b_lo = J.b_hi + x_plane; J.b_blk = blk_bytes(rows_x(L, l)); J.n = rows_x(L, l);
         J.out = g_w[l]; J.ld = layer_in(L, l); J.transposed = 0; J.m_off = mh * 128; J.m_valid = kWidth;
         J.n_valid = layer_in(L, l); J.bias_out = g_b[l];
       } else {
-        J.a_hi = sv + L.xs_off[5]; J.a_lo = J.a_hi + x_plane; J.a_blk = kWidth * 128; J.a_row_off = mh * 128 * 128;
-        J.b_hi = dy + L.dy_off[5]; J.b_lo = J.b_hi + y_plane; J.b_blk = 16 * 128; J.n = 16;
+        J.a_hi = sv + L.xs_off[5]; J.a_lo = J.a_hi + x_plane; J.a_blk = blk_bytes(kWidth); J.a_row_off = mh * 2 * 8192;
+        J.b_hi = dy + L.dy_off[5]; J.b_lo = J.b_hi + y_plane; J.b_blk = blk_bytes(16); J.n = 16;
         J.out = g_w[5]; J.ld = kWidth; J.transposed = 1; J.m_off = mh * 128; J.m_valid = kWidth; J.n_valid = 3;
         J.bias_out = nullptr;
       }

@@ -40,7 +40,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 23)) {
       printf("dvd_b200: mbarrier wait timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
              (void*)bar, parity);
       __trap();
@@ -90,12 +90,26 @@ __device__ __forceinline__ uint64_t make_sdesc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16: A,B = bf16 (K-major), D = fp32.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// MN-major operand (the MN index is contiguous in memory, K strided), SWIZZLE_128B image:
+// 64-element MN atoms; inside an atom one 128-byte row per K index, 8-row groups of 1024 bytes
+// (SBO), 16-byte chunk c of row r stored at chunk (c ^ (r & 7)); next MN atom `lbo_bytes` further
+// (LBO = rows_of_K * 128). Advancing K by 16 rows = +2048 bytes on the start address.
+__device__ __forceinline__ uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16: A,B = bf16, D = fp32. a_mn / b_mn: operand is MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
   return (1u << 4)                    // c_format = F32
          | (1u << 7)                  // a_format = BF16
          | (1u << 10)                 // b_format = BF16
-         | (0u << 15) | (0u << 16)    // a_major, b_major = K
+         | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16)
          | ((uint32_t)(N >> 3) << 17) // n_dim
          | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
@@ -181,6 +195,14 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
 // byte offset of element (row, k) inside one [rows x 64 bf16] SWIZZLE_128B K-major block
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ row) & 7u) << 4) + (k & 7u) * 2u;
+}
+
+// byte offset of element (mn, k) inside one MN-major SWIZZLE_128B block with 64 K-rows (k < 64)
+__host__ __device__ __forceinline__ uint32_t mn128_offset(uint32_t mn, uint32_t k) {
+  return (mn >> 6) * 8192u + (k >> 3) * 1024u + (k & 7u) * 128u + (((((mn & 63u) >> 3) ^ k) & 7u) << 4) + (mn & 7u) * 2u;
+}
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 }  // namespace tc

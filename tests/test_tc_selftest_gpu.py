@@ -22,13 +22,13 @@ def run_selftest(K, N, mode, passes, seed=0):
     return float((D.double() - ref).abs().max() / ref.abs().max())
 
 
-@pytest.mark.parametrize('mode', [0, 1])
-@pytest.mark.parametrize('K,N', [(64, 256), (128, 256), (128, 16), (64, 64)])
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('K,N', [(64, 256), (128, 256), (128, 16), (64, 64), (64, 144)])
 def test_umma_bf16x3_is_fp32_grade(K, N, mode):
     assert run_selftest(K, N, mode, 3) < 2e-5
 
 
-@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('mode', [0, 1, 2])
 def test_umma_single_pass_is_bf16_grade(mode):
     e = run_selftest(128, 256, mode, 1)
     assert 1e-4 < e < 2e-2
