@@ -17,6 +17,7 @@
 // bwd 48 (the same 32 read + g_sf 12 + g_d2 4 written). See DESIGN.md for the full accounting.
 #include "common.cuh"
 #include <initializer_list>
+#include <stdlib.h>
 
 namespace dvd {
 
@@ -549,6 +550,11 @@ static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs
   bool al = true;
   for (const void* p : ptrs) al = al && (p == nullptr || aligned16(p));
   long total = (long)B * H * W;
+  if (const char* ev = getenv("DVD_REPROJECT_VEC")) {   // tuning override: 1, 2 or 4
+    int v = atoi(ev);
+    if ((v == 4 && al && W % 4 == 0) || (v == 2 && al && W % 2 == 0)) return v;
+    if (v == 1) return 1;
+  }
   // wide vectors only when enough threads remain to cover HBM latency (>= 512 / 256 threads per SM)
   if (al && W % 4 == 0 && total / 4 >= (long)num_sms() * 512) return 4;
   if (al && W % 2 == 0 && total / 2 >= (long)num_sms() * 256) return 2;

@@ -65,42 +65,38 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackParams P) {
 
 // =============================================================================================
 // periodic embedding (M1), feature order of SceneFlowFieldNet.forward: cat([t_emb, xyz_emb])
+//   t_emb   = [t, cos(ft_k t) k<FT, sin(ft_k t) k<FT]                       (NT = 1 + 2 FT, if time dependent)
+//   xyz_emb = [x, y, z, cos(f_k x), cos(f_k y), cos(f_k z) k<FX, sin(...) k<FX]
+// Loops over the frequencies are deliberately NOT unrolled: a fully unrolled epilogue was ~0.5 MB of SASS and
+// spent 30 % of its issue slots waiting for the instruction cache (profiles/r1_mlp_fwd_v1_*.txt).
 template <int FX, int FT, bool TD>
 struct Embed {
   static constexpr int NT = TD ? 1 + 2 * FT : 0;
   static constexpr int NIN = NT + 3 + 6 * FX;
   static constexpr int KPAD = (NIN + 15) / 16 * 16;
-  float t, x[3];
-  float ct[FT > 0 ? FT : 1], st[FT > 0 ? FT : 1];
-  float cx[FX > 0 ? FX : 1][3], sx[FX > 0 ? FX : 1][3];
+  // fast path: cos block starts at an even feature index, so two frequencies give exactly three packed words
+  static constexpr bool kPaired = ((NT + 3) % 2 == 0) && (FX % 2 == 0);
 
-  __device__ __forceinline__ void compute(const dvd_mlp_cfg& c, float t_, float x0, float x1, float x2) {
-    t = t_; x[0] = x0; x[1] = x1; x[2] = x2;
-    if (TD) {
-#pragma unroll
-      for (int k = 0; k < FT; ++k) sincosf(c.freq_t[k] * t_, &st[k], &ct[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < FX; ++k) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) sincosf(c.freq_xyz[k] * x[d], &sx[k][d], &cx[k][d]);
-    }
-  }
-  // j must be a compile-time constant after unrolling
-  __device__ __forceinline__ float get(int j) const {
+  // feature j (runtime index)
+  static __device__ __forceinline__ float feature(const dvd_mlp_cfg& c, int j, float t, float x, float y, float z) {
+    float s, co;
     if (j < NT) {
       if (j == 0) return t;
-      j -= 1;
-      if (j < FT) return ct[j];
-      return st[j - FT];
+      int k = j - 1;
+      const bool is_sin = k >= FT;
+      if (is_sin) k -= FT;
+      fast_sincos(c.freq_t[k] * t, s, co);
+      return is_sin ? s : co;
     }
     j -= NT;
-    if (j < 3) return x[j];
+    if (j < 3) return j == 0 ? x : (j == 1 ? y : z);
     j -= 3;
-    if (j < 3 * FX) return cx[j / 3][j % 3];
-    j -= 3 * FX;
-    if (j < 3 * FX) return sx[j / 3][j % 3];
-    return 0.f;
+    if (j >= 6 * FX) return 0.f;
+    const bool is_sin = j >= 3 * FX;
+    if (is_sin) j -= 3 * FX;
+    const int k = j / 3, d = j - 3 * k;
+    fast_sincos(c.freq_xyz[k] * (d == 0 ? x : (d == 1 ? y : z)), s, co);
+    return is_sin ? s : co;
   }
 };
 
@@ -273,25 +269,40 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
         }
         // ---- embedding -> A operand (layer 0 input)
         {
-          E emb;
-          emb.compute(P.cfg, t, px, py, pz);
           uint8_t* x0_hi = SAVE ? save_e + L.xs_off[0] + (size_t)chunk * blk_bytes(E::KPAD) : nullptr;
           uint8_t* x0_lo = SAVE ? x0_hi + (size_t)L.nq * blk_bytes(E::KPAD) : nullptr;
-#pragma unroll
-          for (int w0 = 0; w0 < E::KPAD / 2; w0 += 8) {
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) split2(emb.get(2 * (w0 + j)), emb.get(2 * (w0 + j) + 1), hi[j], lo[j]);
-            tmem_st8(tAhi + w0, hi);
-            tmem_st8(tAlo + w0, lo);
-            if (SAVE) {   // 16 channels = two 16-byte chunks of this pixel's row
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint32_t o = mn128_offset(2 * w0 + 8 * h, kq);
-                st_global_v4(x0_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
-                st_global_v4(x0_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
-              }
+          auto emit = [&](int w, float f0, float f1) {
+            uint32_t hi, lo;
+            split2(f0, f1, hi, lo);
+            tmem_st1(tAhi + w, hi);
+            tmem_st1(tAlo + w, lo);
+            if (SAVE) {
+              const uint32_t o = mn128_offset(2 * w, kq);
+              *reinterpret_cast<uint32_t*>(x0_hi + o) = hi;
+              *reinterpret_cast<uint32_t*>(x0_lo + o) = lo;
             }
+          };
+          if (E::kPaired) {
+            constexpr int W0 = (E::NT + 3) / 2;           // first word of the cos block
+#pragma unroll 1
+            for (int w = 0; w < W0; ++w)
+              emit(w, E::feature(P.cfg, 2 * w, t, px, py, pz), E::feature(P.cfg, 2 * w + 1, t, px, py, pz));
+#pragma unroll 1
+            for (int kp = 0; kp < FX / 2; ++kp) {
+              const float f0 = P.cfg.freq_xyz[2 * kp], f1 = P.cfg.freq_xyz[2 * kp + 1];
+              float s0x, c0x, s0y, c0y, s0z, c0z, s1x, c1x, s1y, c1y, s1z, c1z;
+              fast_sincos(f0 * px, s0x, c0x); fast_sincos(f0 * py, s0y, c0y); fast_sincos(f0 * pz, s0z, c0z);
+              fast_sincos(f1 * px, s1x, c1x); fast_sincos(f1 * py, s1y, c1y); fast_sincos(f1 * pz, s1z, c1z);
+              const int wc = W0 + 3 * kp, ws = W0 + 3 * (FX / 2) + 3 * kp;
+              emit(wc, c0x, c0y); emit(wc + 1, c0z, c1x); emit(wc + 2, c1y, c1z);
+              emit(ws, s0x, s0y); emit(ws + 1, s0z, s1x); emit(ws + 2, s1y, s1z);
+            }
+#pragma unroll 1
+            for (int w = W0 + 3 * FX; w < E::KPAD / 2; ++w) emit(w, 0.f, 0.f);
+          } else {
+#pragma unroll 1
+            for (int w = 0; w < E::KPAD / 2; ++w)
+              emit(w, E::feature(P.cfg, 2 * w, t, px, py, pz), E::feature(P.cfg, 2 * w + 1, t, px, py, pz));
           }
         }
         tmem_st_wait();
@@ -305,8 +316,10 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
           const float* bl = S.bias + l * 256;
           uint8_t* x_hi = SAVE ? save_e + L.xs_off[l + 1] + (size_t)chunk * blk_bytes(kWidth) : nullptr;
           uint8_t* x_lo = SAVE ? x_hi + (size_t)L.nq * blk_bytes(kWidth) : nullptr;
-          uint32_t maskw[8];
-#pragma unroll
+          uint32_t* maskp = SAVE ? reinterpret_cast<uint32_t*>(save_e + L.mask_off +
+                                                              (((size_t)l * L.ntiles + tile) * kTileM + row) * 32)
+                                 : nullptr;
+#pragma unroll 1
           for (int cb = 0; cb < 8; ++cb) {
             const int c0 = cb * 32;
             uint32_t r[32];
@@ -315,15 +328,16 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
             uint32_t hi[16], lo[16], mb = 0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float y0 = __uint_as_float(r[2 * j]) + bl[c0 + 2 * j];
-              float y1 = __uint_as_float(r[2 * j + 1]) + bl[c0 + 2 * j + 1];
-              mb |= (y0 > 0.f ? 1u : 0u) << (2 * j);
-              mb |= (y1 > 0.f ? 1u : 0u) << (2 * j + 1);
-              float x0 = y0 > 0.f ? y0 : y0 * 0.2f;
-              float x1 = y1 > 0.f ? y1 : y1 * 0.2f;
-              split2(x0, x1, hi[j], lo[j]);
+              const float2 bb = *reinterpret_cast<const float2*>(bl + c0 + 2 * j);
+              const float y0 = __uint_as_float(r[2 * j]) + bb.x;
+              const float y1 = __uint_as_float(r[2 * j + 1]) + bb.y;
+              if (SAVE) {
+                mb |= (y0 > 0.f ? 1u : 0u) << (2 * j);
+                mb |= (y1 > 0.f ? 1u : 0u) << (2 * j + 1);
+              }
+              // LeakyReLU(0.2): max(y, 0.2 y)
+              split2(fmaxf(y0, 0.2f * y0), fmaxf(y1, 0.2f * y1), hi[j], lo[j]);
             }
-            maskw[cb] = mb;
             tmem_st16(tAhi + c0 / 2, hi);
             tmem_st16(tAlo + c0 / 2, lo);
             if (SAVE) {   // 32 channels = four 16-byte chunks of this pixel's 128-byte rows
@@ -333,12 +347,8 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
                 st_global_v4(x_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
                 st_global_v4(x_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
               }
+              maskp[cb] = mb;
             }
-          }
-          if (SAVE) {
-            uint4* mp = reinterpret_cast<uint4*>(save_e + L.mask_off + (((size_t)l * L.ntiles + tile) * kTileM + row) * 32);
-            mp[0] = make_uint4(maskw[0], maskw[1], maskw[2], maskw[3]);
-            mp[1] = make_uint4(maskw[4], maskw[5], maskw[6], maskw[7]);
           }
           tmem_st_wait();
           tc_fence_before();
@@ -521,25 +531,23 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
         mbar_wait(S.d_ready, d_phase);
         d_phase ^= 1u;
         tc_fence_after();
-        const uint4* mp = reinterpret_cast<const uint4*>(P.save_e + L.mask_off +
-                                                         (((size_t)(l - 1) * L.ntiles + tile) * kTileM + row) * 32);
-        const uint4 m0 = mp[0], m1 = mp[1];
-        const uint32_t maskw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const uint32_t* maskp = reinterpret_cast<const uint32_t*>(P.save_e + L.mask_off +
+                                                                  (((size_t)(l - 1) * L.ntiles + tile) * kTileM + row) * 32);
         uint8_t* y_hi = P.dy + L.dy_off[l - 1] + (size_t)chunk * blk_bytes(kWidth);
         uint8_t* y_lo = y_hi + (size_t)L.nq * blk_bytes(kWidth);
-#pragma unroll
+#pragma unroll 1
         for (int cb = 0; cb < 8; ++cb) {
           const int c0 = cb * 32;
           uint32_t r[32];
           tmem_ld32(tD + c0, r);
+          const uint32_t mb = maskp[cb];
           tmem_ld_wait();
-          const uint32_t mb = maskw[cb];
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float v0 = __uint_as_float(r[2 * j]), v1 = __uint_as_float(r[2 * j + 1]);
-            v0 = ((mb >> (2 * j)) & 1u) ? v0 : v0 * 0.2f;
-            v1 = ((mb >> (2 * j + 1)) & 1u) ? v1 : v1 * 0.2f;
+            v0 *= ((mb >> (2 * j)) & 1u) ? 1.0f : 0.2f;
+            v1 *= ((mb >> (2 * j + 1)) & 1u) ? 1.0f : 0.2f;
             split2(v0, v1, hi[j], lo[j]);
           }
           tmem_st16(tAhi + c0 / 2, hi);
@@ -568,30 +576,29 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
             for (int k = 0; k < P.e; ++k) t += P.dt;   // same fp32 accumulation as the forward chain
           }
         }
-        E emb;
-        emb.compute(P.cfg, t, px, py, pz);
-        float gp[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c0 = 0; c0 < E::KPAD; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tD + c0, r);
+        float gpx = 0.f, gpy = 0.f, gpz = 0.f;
+        {
+          uint32_t gx, gy, gz;
+          tmem_ld1(tD + E::NT, gx); tmem_ld1(tD + E::NT + 1, gy); tmem_ld1(tD + E::NT + 2, gz);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int f = c0 + j - E::NT;   // index inside the xyz embedding
-            if (f < 0 || f >= 3 + 6 * FX) continue;
-            const float gv = __uint_as_float(r[j]);
-            if (f < 3) {
-              gp[f] += gv;
-            } else if (f < 3 + 3 * FX) {
-              const int k = (f - 3) / 3, d = (f - 3) % 3;
-              gp[d] -= gv * P.cfg.freq_xyz[k] * emb.sx[k][d];
-            } else {
-              const int k = (f - 3 - 3 * FX) / 3, d = (f - 3 - 3 * FX) % 3;
-              gp[d] += gv * P.cfg.freq_xyz[k] * emb.cx[k][d];
-            }
-          }
+          gpx = __uint_as_float(gx); gpy = __uint_as_float(gy); gpz = __uint_as_float(gz);
         }
+        constexpr int CB = E::NT + 3, SB = E::NT + 3 + 3 * FX;   // first cos / sin feature
+#pragma unroll 1
+        for (int k = 0; k < FX; ++k) {
+          uint32_t gc[3], gs[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { tmem_ld1(tD + CB + 3 * k + d, gc[d]); tmem_ld1(tD + SB + 3 * k + d, gs[d]); }
+          const float f = P.cfg.freq_xyz[k];
+          float sx, cx, sy, cy, sz, cz;
+          fast_sincos(f * px, sx, cx); fast_sincos(f * py, sy, cy); fast_sincos(f * pz, sz, cz);
+          tmem_ld_wait();
+          // d/dx cos(f x) = -f sin(f x) ; d/dx sin(f x) = f cos(f x)
+          gpx += f * (__uint_as_float(gs[0]) * cx - __uint_as_float(gc[0]) * sx);
+          gpy += f * (__uint_as_float(gs[1]) * cy - __uint_as_float(gc[1]) * sy);
+          gpz += f * (__uint_as_float(gs[2]) * cz - __uint_as_float(gc[2]) * sz);
+        }
+        const float gp[3] = {gpx, gpy, gpz};
         if (valid && P.a_out) {
           P.a_out[pidx] = ain_x + gp[0];
           P.a_out[pidx + P.hw] = ain_y + gp[1];

@@ -179,6 +179,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r0) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r0) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r0) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- fp32 -> (hi, lo) bf16 split:  x ~= hi + lo with |x - hi - lo| <= 2^-17 |x| -------------------
@@ -190,6 +196,17 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// sin / cos with a two-constant Cody-Waite reduction to [-pi, pi] followed by the MUFU approximations:
+// absolute error ~5e-7 for |a| < 2^13 (embedding arguments are f_k * coordinate, f_k <= 17), i.e. below the
+// rounding error the fp32 product f_k * x already carries; no slow path, no local memory.
+__device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {
+  const float n = rintf(a * 0.15915494309189535f);
+  float r = fmaf(-n, 6.28318548202514648f, a);        // 2*pi rounded to fp32
+  r = fmaf(-n, -1.74845553e-7f, r);                   // 2*pi - fp32(2*pi)
+  s = __sinf(r);
+  c = __cosf(r);
 }
 
 // byte offset of element (row, k) inside one [rows x 64 bf16] SWIZZLE_128B K-major block
