@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(kThreads) reproject_materialize_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs) {
+static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs, int max_vec = 4) {
   bool al = true;
   for (const void* p : ptrs) al = al && (p == nullptr || aligned16(p));
   long total = (long)B * H * W;
@@ -556,8 +556,8 @@ static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs
     if (v == 1) return 1;
   }
   // wide vectors only when enough threads remain to cover HBM latency (>= 512 / 256 threads per SM)
-  if (al && W % 4 == 0 && total / 4 >= (long)num_sms() * 512) return 4;
-  if (al && W % 2 == 0 && total / 2 >= (long)num_sms() * 256) return 2;
+  if (max_vec >= 4 && al && W % 4 == 0 && total / 4 >= (long)num_sms() * 512) return 4;
+  if (max_vec >= 2 && al && W % 2 == 0 && total / 2 >= (long)num_sms() * 256) return 2;
   return 1;
 }
 
@@ -653,7 +653,9 @@ extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2
   DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && mask_2 && sf && poses && scalars && g_sf, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_depth_2) DVD_CUDA_CALL(cudaMemsetAsync(g_depth_2, 0, (size_t)B * H * W * sizeof(float), st));
-  int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2, g_sf});
+  // measured on B200 (profiles/r1_reproject_vec_sweep.txt): the scatter-add backward is fastest with one pixel per
+  // thread (1.97 TB/s vs 1.28 / 1.46 for 2 / 4): more warps in flight hide the red.global latency
+  int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2, g_sf}, 1);
   dim3 g = grid_for(B, H * W / vec);
   if (vec == 4) reproject_loss_bwd_kernel<4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
   else if (vec == 2) reproject_loss_bwd_kernel<2><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);

@@ -13,7 +13,8 @@
 // async copies of pre-swizzled blocks (see sf_mlp_layout.cuh), consumed by single-thread tcgen05.mma.
 // fp32 accuracy comes from the bf16 (hi, lo) split: D += Ahi*Bhi + Alo*Bhi + Ahi*Blo.
 // Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue
-// (TMEM -> registers: bias, LeakyReLU, hi/lo split -> TMEM; embedding; Euler update).
+// (TMEM -> registers: bias, LeakyReLU, hi/lo split -> TMEM; embedding; Euler update); two warps share a TMEM
+// lane quarter and split the 256 columns, each keeping its own copy of the per-pixel state.
 #include "common.cuh"
 #include "sf_mlp_layout.cuh"
 #include "tc_common.cuh"
@@ -23,7 +24,9 @@ using namespace tc;
 
 constexpr int kStages = 6;
 constexpr uint32_t kStageBytes = 32768;
-constexpr int kThreadsMlp = 192;
+constexpr int kEpiWarps = 8;                       // two epilogue warps per TMEM lane quarter (column halves)
+constexpr int kThreadsMlp = 32 * (2 + kEpiWarps);   // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
+constexpr int kThreadsWgrad = 192;
 constexpr uint32_t kColD = 0, kColAhi = 256, kColAlo = 384;
 
 // =============================================================================================
@@ -104,13 +107,14 @@ struct Embed {
 struct ChainSmem {
   uint8_t* stage[kStages];
   float* bias;           // 5*256 + 16
+  float* xchg;           // [128][4] partial point gradients exchanged between the two warps of a lane quarter
   uint64_t* w_full;      // [kStages]
   uint64_t* w_empty;     // [kStages]
   uint64_t* a_ready;
   uint64_t* d_ready;
   uint32_t* tmem_holder;
 };
-constexpr size_t kChainSmemBytes = 1024 + (size_t)kStages * kStageBytes + (5 * 256 + 16) * 4 + 256;
+constexpr size_t kChainSmemBytes = 1024 + (size_t)kStages * kStageBytes + (5 * 256 + 16) * 4 + 128 * 4 * 4 + 256;
 
 __device__ __forceinline__ ChainSmem carve(uint8_t* raw) {
   ChainSmem s;
@@ -119,6 +123,8 @@ __device__ __forceinline__ ChainSmem carve(uint8_t* raw) {
   p += (size_t)kStages * kStageBytes;
   s.bias = reinterpret_cast<float*>(p);
   p += (5 * 256 + 16) * 4;
+  s.xchg = reinterpret_cast<float*>(p);
+  p += 128 * 4 * 4;
   s.w_full = reinterpret_cast<uint64_t*>(p);
   s.w_empty = s.w_full + kStages;
   s.a_ready = s.w_empty + kStages;
@@ -135,7 +141,7 @@ __device__ __forceinline__ void chain_setup(ChainSmem& s, int warp, int lane) {
       mbar_init(&s.w_full[i], 1);
       mbar_init(&s.w_empty[i], 1);
     }
-    mbar_init(s.a_ready, 128);
+    mbar_init(s.a_ready, 32 * kEpiWarps);
     mbar_init(s.d_ready, 1);
     fence_mbar_init();
   }
@@ -242,8 +248,9 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
       }
     }
   } else {
-    // ===== epilogue warps: one pixel per thread =====
+    // ===== epilogue warps: one pixel per thread, two warps (column halves) per lane quarter =====
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t tD = tmem + kColD + lane_base, tAhi = tmem + kColAhi + lane_base, tAlo = tmem + kColAlo + lane_base;
@@ -263,7 +270,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
       const uint32_t kq = (uint32_t)(row & 63);
       for (int e = 0; e < P.n_eval; ++e) {
         uint8_t* save_e = SAVE ? P.save + (size_t)e * L.save_total : nullptr;
-        if (SAVE && valid) {
+        if (SAVE && valid && hsel == 0) {
           float* ps = P.p_steps + (size_t)e * P.npx * 3 + pidx;
           ps[0] = px; ps[P.hw] = py; ps[2 * P.hw] = pz;
         }
@@ -284,11 +291,14 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
           };
           if (E::kPaired) {
             constexpr int W0 = (E::NT + 3) / 2;           // first word of the cos block
+            constexpr int KSPLIT = (FX / 2) * 3 / 8;      // warp 0 of the pair: t-part + first frequencies
+            if (hsel == 0) {
 #pragma unroll 1
-            for (int w = 0; w < W0; ++w)
-              emit(w, E::feature(P.cfg, 2 * w, t, px, py, pz), E::feature(P.cfg, 2 * w + 1, t, px, py, pz));
+              for (int w = 0; w < W0; ++w)
+                emit(w, E::feature(P.cfg, 2 * w, t, px, py, pz), E::feature(P.cfg, 2 * w + 1, t, px, py, pz));
+            }
 #pragma unroll 1
-            for (int kp = 0; kp < FX / 2; ++kp) {
+            for (int kp = (hsel == 0 ? 0 : KSPLIT); kp < (hsel == 0 ? KSPLIT : FX / 2); ++kp) {
               const float f0 = P.cfg.freq_xyz[2 * kp], f1 = P.cfg.freq_xyz[2 * kp + 1];
               float s0x, c0x, s0y, c0y, s0z, c0z, s1x, c1x, s1y, c1y, s1z, c1z;
               fast_sincos(f0 * px, s0x, c0x); fast_sincos(f0 * py, s0y, c0y); fast_sincos(f0 * pz, s0z, c0z);
@@ -297,11 +307,14 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
               emit(wc, c0x, c0y); emit(wc + 1, c0z, c1x); emit(wc + 2, c1y, c1z);
               emit(ws, s0x, s0y); emit(ws + 1, s0z, s1x); emit(ws + 2, s1y, s1z);
             }
+            if (hsel == 1) {
 #pragma unroll 1
-            for (int w = W0 + 3 * FX; w < E::KPAD / 2; ++w) emit(w, 0.f, 0.f);
+              for (int w = W0 + 3 * FX; w < E::KPAD / 2; ++w) emit(w, 0.f, 0.f);
+            }
           } else {
+            constexpr int WH = E::KPAD / 4;
 #pragma unroll 1
-            for (int w = 0; w < E::KPAD / 2; ++w)
+            for (int w = hsel * WH; w < (hsel == 0 ? WH : E::KPAD / 2); ++w)
               emit(w, E::feature(P.cfg, 2 * w, t, px, py, pz), E::feature(P.cfg, 2 * w + 1, t, px, py, pz));
           }
         }
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
                                                               (((size_t)l * L.ntiles + tile) * kTileM + row) * 32)
                                  : nullptr;
 #pragma unroll 1
-          for (int cb = 0; cb < 8; ++cb) {
+          for (int cb = hsel * 4; cb < hsel * 4 + 4; ++cb) {
             const int c0 = cb * 32;
             uint32_t r[32];
             tmem_ld32(tD + c0, r);
@@ -366,7 +379,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
           const float sx = (__uint_as_float(r[0]) + b5[0]) / P.cfg.sf_mag_div;
           const float sy = (__uint_as_float(r[1]) + b5[1]) / P.cfg.sf_mag_div;
           const float sz = (__uint_as_float(r[2]) + b5[2]) / P.cfg.sf_mag_div;
-          if (valid && P.s_steps) {
+          if (valid && P.s_steps && hsel == 0) {
             float* ss = P.s_steps + (size_t)e * P.npx * 3 + pidx;
             ss[0] = sx; ss[P.hw] = sy; ss[2 * P.hw] = sz;
           }
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
           t += P.dt;
         }
       }
-      if (valid && P.acc) {
+      if (valid && P.acc && hsel == 0) {
         float* ao = P.acc + pidx;
         ao[0] = ax; ao[P.hw] = ay; ao[2 * P.hw] = az;
       }
@@ -484,6 +497,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
     }
   } else {
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t tD = tmem + kColD + lane_base, tAhi = tmem + kColAhi + lane_base, tAlo = tmem + kColAlo + lane_base;
@@ -505,8 +519,8 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
       }
       // dY_5 = gs / sf_mag_div (3 of 16 padded columns)
       const float d5x = gx / P.cfg.sf_mag_div, d5y = gy / P.cfg.sf_mag_div, d5z = gz / P.cfg.sf_mag_div;
-      b5x += d5x; b5y += d5y; b5z += d5z;
-      {
+      if (hsel == 0) {
+        b5x += d5x; b5y += d5y; b5z += d5z;
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { hi[j] = 0; lo[j] = 0; }
@@ -536,7 +550,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
         uint8_t* y_hi = P.dy + L.dy_off[l - 1] + (size_t)chunk * blk_bytes(kWidth);
         uint8_t* y_lo = y_hi + (size_t)L.nq * blk_bytes(kWidth);
 #pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
+        for (int cb = hsel * 4; cb < hsel * 4 + 4; ++cb) {
           const int c0 = cb * 32;
           uint32_t r[32];
           tmem_ld32(tD + c0, r);
@@ -577,7 +591,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
           }
         }
         float gpx = 0.f, gpy = 0.f, gpz = 0.f;
-        {
+        if (hsel == 0) {
           uint32_t gx, gy, gz;
           tmem_ld1(tD + E::NT, gx); tmem_ld1(tD + E::NT + 1, gy); tmem_ld1(tD + E::NT + 2, gz);
           tmem_ld_wait();
@@ -585,7 +599,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
         }
         constexpr int CB = E::NT + 3, SB = E::NT + 3 + 3 * FX;   // first cos / sin feature
 #pragma unroll 1
-        for (int k = 0; k < FX; ++k) {
+        for (int k = hsel * (FX / 2); k < (hsel == 0 ? FX / 2 : FX); ++k) {
           uint32_t gc[3], gs[3];
 #pragma unroll
           for (int d = 0; d < 3; ++d) { tmem_ld1(tD + CB + 3 * k + d, gc[d]); tmem_ld1(tD + SB + 3 * k + d, gs[d]); }
@@ -598,8 +612,16 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
           gpy += f * (__uint_as_float(gs[1]) * cy - __uint_as_float(gc[1]) * sy);
           gpz += f * (__uint_as_float(gs[2]) * cz - __uint_as_float(gc[2]) * sz);
         }
+        // combine the two frequency halves of this pixel through shared memory (pair-wise named barrier)
+        if (hsel == 1) {
+          S.xchg[row * 4 + 0] = gpx; S.xchg[row * 4 + 1] = gpy; S.xchg[row * 4 + 2] = gpz;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        if (hsel == 0) {
+          gpx += S.xchg[row * 4 + 0]; gpy += S.xchg[row * 4 + 1]; gpz += S.xchg[row * 4 + 2];
+        }
         const float gp[3] = {gpx, gpy, gpz};
-        if (valid && P.a_out) {
+        if (valid && P.a_out && hsel == 0) {
           P.a_out[pidx] = ain_x + gp[0];
           P.a_out[pidx + P.hw] = ain_y + gp[1];
           P.a_out[pidx + 2 * P.hw] = ain_z + gp[2];
@@ -608,7 +630,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
     }
     // output-layer bias gradient: warp reduce, one atomic per warp
     b5x = warp_sum(b5x); b5y = warp_sum(b5y); b5z = warp_sum(b5z);
-    if (lane == 0 && P.g_bias5) {
+    if (lane == 0 && P.g_bias5 && hsel == 0) {
       atomicAdd(P.g_bias5 + 0, b5x);
       atomicAdd(P.g_bias5 + 1, b5y);
       atomicAdd(P.g_bias5 + 2, b5z);
@@ -643,7 +665,7 @@ constexpr int kWgStages = 2;
 constexpr uint32_t kWgStageBytes = 2 * 16384 + 2 * 32768;
 constexpr size_t kWgradSmemBytes = 1024 + (size_t)kWgStages * kWgStageBytes + 8192 + 256;
 
-__global__ void __launch_bounds__(kThreadsMlp, 1) mlp_wgrad_kernel(const __grid_constant__ WgradParams P) {
+__global__ void __launch_bounds__(kThreadsWgrad, 1) mlp_wgrad_kernel(const __grid_constant__ WgradParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage[kWgStages];
@@ -946,7 +968,7 @@ extern "C" int dvd_mlp_wgrad(const dvd_mlp_cfg* cfg, const void* save_e, const v
   if (ksplit < 1) ksplit = 1;
   if ((long)ksplit > L.nq) ksplit = (int)L.nq;
   DVD_CUDA_CALL(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmemBytes));
-  mlp_wgrad_kernel<<<dim3(nj, ksplit), kThreadsMlp, kWgradSmemBytes, (cudaStream_t)stream>>>(P);
+  mlp_wgrad_kernel<<<dim3(nj, ksplit), kThreadsWgrad, kWgradSmemBytes, (cudaStream_t)stream>>>(P);
   DVD_CUDA_LAUNCH_CHECK("mlp_wgrad");
   return 0;
 }
