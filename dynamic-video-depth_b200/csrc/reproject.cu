@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(kThreads) unproject_bwd_kernel(const float* __
 
 // ---------------------------------------------------------------------------------------------
 // fused forward: loss partial sums only
-template <int VEC>
-__global__ void __launch_bounds__(kThreads) reproject_loss_fwd_kernel(
+template <int VEC, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) reproject_loss_fwd_kernel(
     const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
     const float* __restrict__ mask_2, const float* __restrict__ sf, const float* __restrict__ poses,
     dvd_loss_cfg cfg, float* __restrict__ partials, int H, int W) {
@@ -635,9 +635,11 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
   cudaStream_t st = (cudaStream_t)stream;
   int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2});
   dim3 g = grid_for(B, H * W / vec);
-  if (vec == 4) reproject_loss_fwd_kernel<4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
-  else if (vec == 2) reproject_loss_fwd_kernel<2><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
-  else reproject_loss_fwd_kernel<1><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+  static const int minb = getenv("DVD_REPROJECT_MINB") ? atoi(getenv("DVD_REPROJECT_MINB")) : 3;
+  if (vec == 4 && minb >= 4) reproject_loss_fwd_kernel<4, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+  else if (vec == 4) reproject_loss_fwd_kernel<4, 3><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+  else if (vec == 2) reproject_loss_fwd_kernel<2, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+  else reproject_loss_fwd_kernel<1, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
   DVD_CUDA_LAUNCH_CHECK("reproject_loss_fwd");
   reproject_finalize_kernel<<<1, 256, 0, st>>>(partials, (int)(g.x * g.y), *cfg, scalars);
   DVD_CUDA_LAUNCH_CHECK("reproject_finalize");

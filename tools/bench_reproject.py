@@ -28,10 +28,10 @@ def timeit(fn, iters=20, flush=None):
     return ts[len(ts) // 2], ts[0]
 
 
-def main(B=64, H=224, W=384):
+def main(B=64, H=224, W=384, smooth=False):
     from dvd_b200 import ops, synthetic
     dev = 'cuda'
-    one = synthetic.make_batch([(4, 8)], H=H, W=W, seed=0, leading_dim=False)
+    one = synthetic.make_batch([(4, 8)], H=H, W=W, seed=0, leading_dim=False, smooth_flow=smooth)
     rep = lambda t: t.to(dev).repeat(B, *([1] * (t.dim() - 1))).contiguous()  # noqa: E731
     flow, mask = rep(one['flow_1_2']), rep(one['mask_2'].reshape(1, H, W))
     poses = rep(ops.pack_poses_from_batch({k: v for k, v in one.items() if torch.is_tensor(v)}))
@@ -55,8 +55,9 @@ def main(B=64, H=224, W=384):
                      'GBps_best': px * bpp / best / 1e9, 'bytes_per_px': bpp}
         print(name, res[name], flush=True)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    json.dump({'B': B, 'H': H, 'W': W, 'results': res}, open(os.path.join(ROOT, 'gpurun_out', 'bench_reproject.json'), 'w'), indent=1)
+    json.dump({'B': B, 'H': H, 'W': W, 'smooth_flow': smooth, 'results': res},
+              open(os.path.join(ROOT, 'gpurun_out', 'bench_reproject%s.json' % ('_smooth' if smooth else '')), 'w'), indent=1)
 
 
 if __name__ == '__main__':
-    main(B=int(sys.argv[1]) if len(sys.argv) > 1 else 64)
+    main(B=int(sys.argv[1]) if len(sys.argv) > 1 else 64, smooth=len(sys.argv) > 2 and sys.argv[2] == 'smooth')
