@@ -248,8 +248,13 @@ __global__ void __launch_bounds__(kThreads) unproject_fwd_kernel(const float* __
   const float* R = which == 1 ? ps.R1 : ps.R2;
   const float* t = which == 1 ? ps.t1 : ps.t2;
   const int HW = H * W, items = HW / VEC, Wv = W / VEC;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    int y = it / Wv, x0 = (it - y * Wv) * VEC;
+  // (y, xv) walk of the grid-stride loop without a per-iteration integer division
+  const int stride = gridDim.x * blockDim.x, sdy = stride / Wv, sdx = stride - sdy * Wv;
+  int it = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = it / Wv, xv = it - y * Wv;
+  for (; it < items; it += stride, y += sdy, xv += sdx) {
+    if (xv >= Wv) { xv -= Wv; ++y; }
+    const int x0 = xv * VEC;
     size_t pix = (size_t)y * W + x0;
     float d[VEC], ox[VEC], oy[VEC], oz[VEC];
     load_vec<VEC>(depth + (size_t)b * HW + pix, d);
@@ -277,8 +282,13 @@ __global__ void __launch_bounds__(kThreads) unproject_bwd_kernel(const float* __
   __syncthreads();
   const float* R = which == 1 ? ps.R1 : ps.R2;
   const int HW = H * W, items = HW / VEC, Wv = W / VEC;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    int y = it / Wv, x0 = (it - y * Wv) * VEC;
+  // (y, xv) walk of the grid-stride loop without a per-iteration integer division
+  const int stride = gridDim.x * blockDim.x, sdy = stride / Wv, sdx = stride - sdy * Wv;
+  int it = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = it / Wv, xv = it - y * Wv;
+  for (; it < items; it += stride, y += sdy, xv += sdx) {
+    if (xv >= Wv) { xv -= Wv; ++y; }
+    const int x0 = xv * VEC;
     size_t pix = (size_t)y * W + x0;
     float gx[VEC], gy[VEC], gz[VEC], o[VEC];
     const float* g = gP + (size_t)b * 3 * HW + pix;
@@ -311,8 +321,13 @@ __global__ void __launch_bounds__(kThreads, MINB) reproject_loss_fwd_kernel(
   const int HW = H * W, items = HW / VEC, Wv = W / VEC;
   const float* d2img = depth_2 + (size_t)b * HW;
   float s_flow = 0.f, s_disp = 0.f, s_sf = 0.f, s_m = 0.f;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    int y = it / Wv, x0 = (it - y * Wv) * VEC;
+  // (y, xv) walk of the grid-stride loop without a per-iteration integer division
+  const int stride = gridDim.x * blockDim.x, sdy = stride / Wv, sdx = stride - sdy * Wv;
+  int it = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = it / Wv, xv = it - y * Wv;
+  for (; it < items; it += stride, y += sdy, xv += sdx) {
+    if (xv >= Wv) { xv -= Wv; ++y; }
+    const int x0 = xv * VEC;
     size_t pix = (size_t)y * W + x0;
     float d1[VEC], m2[VEC], sx[VEC], sy[VEC], sz[VEC], fx[VEC], fy[VEC];
     load_vec<VEC>(depth_1 + (size_t)b * HW + pix, d1);
@@ -406,8 +421,13 @@ __global__ void __launch_bounds__(kThreads) reproject_loss_bwd_kernel(
   const int HW = H * W, items = HW / VEC, Wv = W / VEC;
   const float* d2img = depth_2 + (size_t)b * HW;
   float* gd2img = g_d2 ? g_d2 + (size_t)b * HW : nullptr;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    int y = it / Wv, x0 = (it - y * Wv) * VEC;
+  // (y, xv) walk of the grid-stride loop without a per-iteration integer division
+  const int stride = gridDim.x * blockDim.x, sdy = stride / Wv, sdx = stride - sdy * Wv;
+  int it = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = it / Wv, xv = it - y * Wv;
+  for (; it < items; it += stride, y += sdy, xv += sdx) {
+    if (xv >= Wv) { xv -= Wv; ++y; }
+    const int x0 = xv * VEC;
     size_t pix = (size_t)y * W + x0;
     float d1[VEC], m2[VEC], sx[VEC], sy[VEC], sz[VEC], fx[VEC], fy[VEC];
     float ox[VEC], oy[VEC], oz[VEC];
@@ -561,10 +581,22 @@ static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs
   return 1;
 }
 
-static dim3 grid_for(int B, int items_per_pair) {
+// One resident wave: blocks = SMs x (CTAs that fit per SM for this kernel), split evenly over the pairs.
+template <typename K>
+static dim3 grid_for(K kernel, int B, int items_per_pair) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) occ = 2;
   int per_pair = (items_per_pair + kThreads - 1) / kThreads;
-  int cap = (num_sms() * 8 + B - 1) / B;  // ~8 resident CTAs of 256 threads per SM over the whole grid
+  int cap = (num_sms() * occ + B - 1) / B;
   if (cap < 1) cap = 1;
+  if (per_pair > cap) per_pair = cap;
+  if (per_pair < 1) per_pair = 1;
+  return dim3((unsigned)per_pair, (unsigned)B, 1);
+}
+// upper bound used to size the partial-sum scratch (8 CTAs per SM is the hardware maximum for 256 threads)
+static dim3 grid_bound(int B, int items_per_pair) {
+  int per_pair = (items_per_pair + kThreads - 1) / kThreads;
+  int cap = (num_sms() * 8 + B - 1) / B;
   if (per_pair > cap) per_pair = cap;
   if (per_pair < 1) per_pair = 1;
   return dim3((unsigned)per_pair, (unsigned)B, 1);
@@ -584,7 +616,7 @@ using namespace dvd;
 extern "C" int dvd_reproject_partials_size(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1) return 0;
   // upper bound over every VEC choice
-  dim3 g = grid_for(B, H * W);
+  dim3 g = grid_bound(B, H * W);
   return (int)(g.x * g.y * 4);
 }
 
@@ -595,10 +627,10 @@ extern "C" int dvd_unproject_fwd(const float* depth, const float* poses, float* 
   DVD_ARG_CHECK(which == 1 || which == 2, "which must be 1 or 2");
   cudaStream_t st = (cudaStream_t)stream;
   int vec = pick_vec(B, H, W, {depth, P});
-  dim3 g = grid_for(B, H * W / vec);
-  if (vec == 4) unproject_fwd_kernel<4><<<g, kThreads, 0, st>>>(depth, poses, P, H, W, which);
-  else if (vec == 2) unproject_fwd_kernel<2><<<g, kThreads, 0, st>>>(depth, poses, P, H, W, which);
-  else unproject_fwd_kernel<1><<<g, kThreads, 0, st>>>(depth, poses, P, H, W, which);
+  const int ipp = H * W / vec;
+  if (vec == 4) unproject_fwd_kernel<4><<<grid_for(unproject_fwd_kernel<4>, B, ipp), kThreads, 0, st>>>(depth, poses, P, H, W, which);
+  else if (vec == 2) unproject_fwd_kernel<2><<<grid_for(unproject_fwd_kernel<2>, B, ipp), kThreads, 0, st>>>(depth, poses, P, H, W, which);
+  else unproject_fwd_kernel<1><<<grid_for(unproject_fwd_kernel<1>, B, ipp), kThreads, 0, st>>>(depth, poses, P, H, W, which);
   DVD_CUDA_LAUNCH_CHECK("unproject_fwd");
   return 0;
 }
@@ -610,10 +642,10 @@ extern "C" int dvd_unproject_bwd(const float* gP, const float* poses, float* gde
   DVD_ARG_CHECK(which == 1 || which == 2, "which must be 1 or 2");
   cudaStream_t st = (cudaStream_t)stream;
   int vec = pick_vec(B, H, W, {gP, gdepth});
-  dim3 g = grid_for(B, H * W / vec);
-  if (vec == 4) unproject_bwd_kernel<4><<<g, kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
-  else if (vec == 2) unproject_bwd_kernel<2><<<g, kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
-  else unproject_bwd_kernel<1><<<g, kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
+  const int ipp = H * W / vec;
+  if (vec == 4) unproject_bwd_kernel<4><<<grid_for(unproject_bwd_kernel<4>, B, ipp), kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
+  else if (vec == 2) unproject_bwd_kernel<2><<<grid_for(unproject_bwd_kernel<2>, B, ipp), kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
+  else unproject_bwd_kernel<1><<<grid_for(unproject_bwd_kernel<1>, B, ipp), kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
   DVD_CUDA_LAUNCH_CHECK("unproject_bwd");
   return 0;
 }
@@ -634,8 +666,13 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
   DVD_ARG_CHECK(aligned16(partials), "partials must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2});
-  dim3 g = grid_for(B, H * W / vec);
+  const int ipp = H * W / vec;
+  dim3 g;
   static const int minb = getenv("DVD_REPROJECT_MINB") ? atoi(getenv("DVD_REPROJECT_MINB")) : 3;
+  if (vec == 4 && minb >= 4) g = grid_for(reproject_loss_fwd_kernel<4, 4>, B, ipp);
+  else if (vec == 4) g = grid_for(reproject_loss_fwd_kernel<4, 3>, B, ipp);
+  else if (vec == 2) g = grid_for(reproject_loss_fwd_kernel<2, 4>, B, ipp);
+  else g = grid_for(reproject_loss_fwd_kernel<1, 4>, B, ipp);
   if (vec == 4 && minb >= 4) reproject_loss_fwd_kernel<4, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
   else if (vec == 4) reproject_loss_fwd_kernel<4, 3><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
   else if (vec == 2) reproject_loss_fwd_kernel<2, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
@@ -658,7 +695,9 @@ extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2
   // measured on B200 (profiles/r1_reproject_vec_sweep.txt): the scatter-add backward is fastest with one pixel per
   // thread (1.97 TB/s vs 1.28 / 1.46 for 2 / 4): more warps in flight hide the red.global latency
   int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2, g_sf}, 1);
-  dim3 g = grid_for(B, H * W / vec);
+  const int ipp = H * W / vec;
+  dim3 g = vec == 4 ? grid_for(reproject_loss_bwd_kernel<4>, B, ipp)
+                    : (vec == 2 ? grid_for(reproject_loss_bwd_kernel<2>, B, ipp) : grid_for(reproject_loss_bwd_kernel<1>, B, ipp));
   if (vec == 4) reproject_loss_bwd_kernel<4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
   else if (vec == 2) reproject_loss_bwd_kernel<2><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
   else reproject_loss_bwd_kernel<1><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
@@ -674,7 +713,7 @@ extern "C" int dvd_reproject_materialize(const float* depth_1, const float* dept
   if (int e = check_shape(B, H, W)) return e;
   DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && poses, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 g = grid_for(B, H * W);
+  dim3 g = grid_for(reproject_materialize_kernel, B, H * W);
   reproject_materialize_kernel<<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, sf, poses, global_p1, sf_by_depth,
                                                        warped_global_p2, warped_p2_camera_2, p1_camera_2, dflow_1_2,
                                                        staticflow_1_2, depth_image_1_2, depth_warp_1_2, H, W);
