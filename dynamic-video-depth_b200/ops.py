@@ -377,3 +377,90 @@ class SceneFlowChain(torch.autograd.Function):
 
 def scene_flow_chain(p0, t0, packed, dt, n_eval, n_acc, weights, biases):
     return SceneFlowChain.apply(p0, t0, packed, float(dt), int(n_eval), int(n_acc), *weights, *biases)
+
+
+# ================================================================================================
+# channels-last glue of the depth nets (csrc/nhwc_ops.cu)
+
+def _is_cl(t):
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _as_cl(t):
+    return t if _is_cl(t) else t.contiguous(memory_format=torch.channels_last)
+
+
+class BnAct(torch.autograd.Function):
+    """Eval-mode BatchNorm (+ residual) (+ ReLU) on channels-last tensors, one pass forward and one backward.
+    forward(x, res|None, gamma, beta, running_mean, running_var, eps, relu) -> y"""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, mean, var, eps, relu):
+        x = _as_cl(x)
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError('BnAct needs float32 CUDA tensors')
+        N, C, H, W = x.shape
+        if C % 4:
+            raise ValueError('channel count must be a multiple of 4')
+        r = _as_cl(res) if res is not None else None
+        y = torch.empty_like(x)   # preserves channels_last
+        lib = _lib.load()
+        LAUNCHES['n'] += 1
+        _lib.check(lib.dvd_bn_act_fwd(_ptr(x), _ptr(r), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), float(eps), _ptr(y),
+                                      N * H * W, C, int(relu), _stream()), 'dvd_bn_act_fwd')
+        ctx.save_for_backward(x, y, gamma, mean, var)
+        ctx.eps, ctx.relu, ctx.has_res = float(eps), bool(relu), res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, gamma, mean, var = ctx.saved_tensors
+        g = _as_cl(g)
+        N, C, H, W = x.shape
+        gx = torch.empty_like(x)
+        gres = torch.empty_like(x) if ctx.has_res else None
+        gg = torch.zeros_like(gamma)
+        gb = torch.zeros_like(gamma)
+        lib = _lib.load()
+        LAUNCHES['n'] += 1
+        _lib.check(lib.dvd_bn_act_bwd(_ptr(g), _ptr(x), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(var), ctx.eps, _ptr(gx), _ptr(gres),
+                                      _ptr(gg), _ptr(gb), N * H * W, C, int(ctx.relu), _stream()), 'dvd_bn_act_bwd')
+        return gx, gres, gg, gb, None, None, None, None
+
+
+def bn_act(x, bn, res=None, relu=True):
+    """`relu(bn(x) + res)` for an nn.BatchNorm2d in eval mode (affine)."""
+    return BnAct.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, relu)
+
+
+class Upsample2x(torch.autograd.Function):
+    """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=...) on channels-last tensors."""
+
+    @staticmethod
+    def forward(ctx, x, align_corners):
+        x = _as_cl(x)
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError('Upsample2x needs float32 CUDA tensors')
+        N, C, H, W = x.shape
+        if C % 4:
+            raise ValueError('channel count must be a multiple of 4')
+        y = torch.empty((N, C, 2 * H, 2 * W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        lib = _lib.load()
+        LAUNCHES['n'] += 1
+        _lib.check(lib.dvd_upsample2x_fwd(_ptr(x), _ptr(y), N, H, W, C, int(align_corners), _stream()), 'dvd_upsample2x_fwd')
+        ctx.shape, ctx.align = (N, C, H, W), bool(align_corners)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _as_cl(g)
+        N, C, H, W = ctx.shape
+        gx = torch.empty((N, C, H, W), dtype=g.dtype, device=g.device, memory_format=torch.channels_last)
+        lib = _lib.load()
+        LAUNCHES['n'] += 1
+        _lib.check(lib.dvd_upsample2x_bwd(_ptr(g), _ptr(gx), N, H, W, C, int(ctx.align), _stream()), 'dvd_upsample2x_bwd')
+        return gx, None
+
+
+def upsample2x(x, align_corners):
+    return Upsample2x.apply(x, bool(align_corners))

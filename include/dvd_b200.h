@@ -162,6 +162,21 @@ int dvd_acc_reg(const float* s0, const float* s1, float acc_mul, float gscale, f
 int dvd_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                   float beta2, float eps, int step, float gscale, void* stream);
 
+/* ---- channels-last (NHWC) glue of the depth nets (D1/D2): tensors are [P = N*H*W pixels][C], C % 4 == 0 ----
+ * eval-mode BatchNorm (the only mode on this path, smf.py:157,168) + optional residual add + optional ReLU:
+ *   y = x*g*rsqrt(var+eps) + (beta - mean*g*rsqrt(var+eps)) (+ res) ; ReLU
+ * replaces torchvision Bottleneck's bn{1,2,3} + relu + `out += identity` and the ATen clamp / add kernels.      */
+int dvd_bn_act_fwd(const float* x, const float* res, const float* gamma, const float* beta, const float* mean,
+                   const float* var, float eps, float* y, long P, int C, int relu, void* stream);
+/* backward: gm = g*[y>0]; gx = gm*scale; gres = gm (may be NULL); ggamma/gbeta are ACCUMULATED (zero them first) */
+int dvd_bn_act_bwd(const float* g, const float* x, const float* y, const float* gamma, const float* mean,
+                   const float* var, float eps, float* gx, float* gres, float* ggamma, float* gbeta,
+                   long P, int C, int relu, void* stream);
+/* x2 bilinear up-sampling (third_party/midas_blocks.py:95-97 align_corners=False; :164-166 align_corners=True;
+ * hourglass UpsamplingBilinear2d = True), NHWC [N,H,W,C] -> [N,2H,2W,C], and its adjoint.                      */
+int dvd_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, int align_corners, void* stream);
+int dvd_upsample2x_bwd(const float* g, float* gx, int N, int H, int W, int C, int align_corners, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
