@@ -25,8 +25,11 @@ class FlatParams:
     nn.Parameter objects are kept — `.data` / `.grad` become views — so `state_dict()` /
     `load_state_dict()` keep working with reference checkpoints."""
 
-    def __init__(self, net):
+    def __init__(self, net, channels_last=False):
+        """channels_last: conv weights with a spatial extent are stored O,kh,kw,I in the flat buffer (logical shape
+        and state-dict values unchanged) so that cuDNN's NHWC kernels take them without a per-call conversion."""
         self.params = [p for p in net.parameters()]
+        self.channels_last = channels_last
         dev = self.params[0].device
         self.offsets, n = [], 0
         for p in self.params:
@@ -36,16 +39,23 @@ class FlatParams:
         self.data = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
         for p, o in zip(self.params, self.offsets):
-            view = self.data[o:o + p.numel()].view(p.shape)
+            view = self._view(self.data, p, o)
             view.copy_(p.data)
             p.data = view
-            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+            p.grad = self._view(self.grad, p, o)
+
+    def _view(self, buf, p, o):
+        flat = buf[o:o + p.numel()]
+        if self.channels_last and p.dim() == 4 and p.shape[2] * p.shape[3] > 1:
+            O, I, kh, kw = p.shape
+            return flat.view(O, kh, kw, I).permute(0, 3, 1, 2)
+        return flat.view(p.shape)
 
     def zero_grad(self):
         self.grad.zero_()
         for p, o in zip(self.params, self.offsets):   # autograd may have swapped the .grad tensor
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
-                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o or p.grad.stride() != p.data.stride():
+                p.grad = self._view(self.grad, p, o)
 
     def broadcast(self, src=0):
         """One flat broadcast instead of one per tensor (train.py:290-292)."""
@@ -91,8 +101,8 @@ class FlatAdam:
         if self.step_count > 0:
             for i, (p, o) in enumerate(zip(self.flat.params, self.flat.offsets)):
                 state[i] = {'step': torch.tensor(float(self.step_count)),
-                            'exp_avg': self.exp_avg[o:o + p.numel()].view(p.shape).clone(),
-                            'exp_avg_sq': self.exp_avg_sq[o:o + p.numel()].view(p.shape).clone()}
+                            'exp_avg': self.flat._view(self.exp_avg, p, o).clone(memory_format=torch.contiguous_format),
+                            'exp_avg_sq': self.flat._view(self.exp_avg_sq, p, o).clone(memory_format=torch.contiguous_format)}
         return {'state': state, 'param_groups': [dict(g) for g in self.param_groups]}
 
     def load_state_dict(self, sd, keep_training_params=True):
@@ -100,8 +110,8 @@ class FlatAdam:
         for i, st in sd.get('state', {}).items():
             i = int(i)
             p, o = self.flat.params[i], self.flat.offsets[i]
-            self.exp_avg[o:o + p.numel()].view(p.shape).copy_(st['exp_avg'])
-            self.exp_avg_sq[o:o + p.numel()].view(p.shape).copy_(st['exp_avg_sq'])
+            self.flat._view(self.exp_avg, p, o).copy_(st['exp_avg'])
+            self.flat._view(self.exp_avg_sq, p, o).copy_(st['exp_avg_sq'])
             steps.append(int(float(st['step'])))
         self.step_count = max(steps) if steps else 0
         if not keep_training_params and sd.get('param_groups'):

@@ -56,13 +56,13 @@ class _AccReg(torch.autograd.Function):
 class _DeferredAdam:
     """Adam whose flat buffers are created when the model reaches its device (`Model.to`)."""
 
-    def __init__(self, net, lr, betas):
-        self.net, self.lr, self.betas = net, lr, betas
+    def __init__(self, net, lr, betas, channels_last=False):
+        self.net, self.lr, self.betas, self.channels_last = net, lr, betas, channels_last
         self.flat, self.adam, self._pending = None, None, None
 
     def materialize(self):
         if self.adam is None:
-            self.flat = FlatParams(self.net)
+            self.flat = FlatParams(self.net, channels_last=self.channels_last)
             self.adam = FlatAdam(self.flat, self.lr, self.betas)
             if self._pending is not None:
                 self.adam.load_state_dict(self._pending)
@@ -144,7 +144,7 @@ class Model(NetInterface):
                                                N_freq_xyz=opt.n_freq_xyz, N_freq_t=opt.n_freq_t)
         self.global_rank = getattr(opt, 'global_rank', 0)
         self._nets = [self.net_depth, self.net_sceneflow]
-        self.optimizer_depth = _DeferredAdam(self.net_depth, opt.lr, self.optim_params['betas'])
+        self.optimizer_depth = _DeferredAdam(self.net_depth, opt.lr, self.optim_params['betas'], channels_last=bool(opt.midas))
         self.optimizer_scene = _DeferredAdam(self.net_sceneflow, opt.lr * opt.scene_lr_mul, self.optim_params['betas'])
         self._optimizers = [self.optimizer_depth, self.optimizer_scene]
         self._metrics = ['flow_loss_1_2', 'loss', 'disp_loss_1_2', 'data_time', 'acc_reg', 'sf_loss']
