@@ -327,9 +327,9 @@ def run_b200_arm(args):
         ops.LAUNCHES['n'] = 0
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        torch.cuda.nvtx.range_push('dvd_timed')     # lets `ncu --nvtx --nvtx-include "dvd_timed/"` list exactly the timed launches
+        torch.cuda.profiler.start()      # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed launches
         logs = [model._train_on_batch(EPOCH, Wm + s, batches[Wm + s]) for s in range(K)]
-        torch.cuda.nvtx.range_pop()
+        torch.cuda.profiler.stop()
         b.record()
         barrier()
         clocks = sampler.stop() if sampler else None

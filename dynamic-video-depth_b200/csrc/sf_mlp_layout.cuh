@@ -41,8 +41,15 @@ __host__ __device__ inline int nkc_f(const MlpLayout& L, int l) { return l == 0 
 __host__ __device__ inline int nkc_b(int l) { return l == 5 ? 1 : 4; }
 __host__ __device__ inline int rows_x(const MlpLayout& L, int l) { return l == 0 ? L.kpad0 : kWidth; }
 __host__ __device__ inline int rows_dy(int l) { return l == 5 ? 16 : kWidth; }
-// bytes of one 64-pixel block of an activation / dY array with `rows` channels (64-channel atoms of 8 KB)
-__host__ __device__ inline uint32_t blk_bytes(int rows) { return (uint32_t)((rows + 63) / 64) * 8192u; }
+// Layout of the saved activation / dY blocks (operands of the weight-gradient GEMM, K = 64 pixels per block):
+//   true : MN-major without swizzle ("interleave", tc_common.cuh: il_offset) — a warp's 32 pixel-owning threads
+//          write 512 contiguous bytes per 16-byte store;
+//   false: MN-major SWIZZLE_128B (mn128_offset) — each thread writes 16-byte pieces of its own 128-byte rows.
+constexpr bool kActInterleave = true;
+// bytes of one 64-pixel block of an activation / dY array with `rows` channels
+__host__ __device__ inline uint32_t blk_bytes(int rows) {
+  return kActInterleave ? (uint32_t)((rows + 7) / 8) * 1024u : (uint32_t)((rows + 63) / 64) * 8192u;
+}
 __host__ __device__ inline int layer_in(const MlpLayout& L, int l) { return l == 0 ? L.nin : kWidth; }
 __host__ __device__ inline int layer_out(int l) { return l == 5 ? 3 : kWidth; }
 

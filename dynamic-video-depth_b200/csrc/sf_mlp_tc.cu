@@ -22,6 +22,13 @@
 namespace dvd {
 using namespace tc;
 
+__host__ __device__ __forceinline__ uint32_t act_offset(uint32_t ch, uint32_t px) {
+  return kActInterleave ? il_offset(ch, px) : mn128_offset(ch, px);
+}
+__device__ __forceinline__ uint64_t act_desc(uint32_t smem_addr, int ks) {
+  return kActInterleave ? make_sdesc_mn_interleave(smem_addr + ks * 256, 1024) : make_sdesc_mn_sw128(smem_addr + ks * 2048, 8192);
+}
+
 constexpr int kStages = 6;
 constexpr uint32_t kStageBytes = 32768;
 constexpr int kEpiWarps = 8;                       // two epilogue warps per TMEM lane quarter (column halves)
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
             tmem_st1(tAhi + w, hi);
             tmem_st1(tAlo + w, lo);
             if (SAVE) {
-              const uint32_t o = mn128_offset(2 * w, kq);
+              const uint32_t o = act_offset(2 * w, kq);
               *reinterpret_cast<uint32_t*>(x0_hi + o) = hi;
               *reinterpret_cast<uint32_t*>(x0_lo + o) = lo;
             }
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
             if (SAVE) {   // 32 channels = four 16-byte chunks of this pixel's 128-byte rows
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
-                const uint32_t o = mn128_offset(c0 + 8 * h, kq);
+                const uint32_t o = act_offset(c0 + 8 * h, kq);
                 st_global_v4(x_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
                 st_global_v4(x_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
               }
@@ -532,7 +539,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
         uint8_t* y_lo = y_hi + (size_t)L.nq * blk_bytes(16);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint32_t o = mn128_offset(8 * h, kq);
+          const uint32_t o = act_offset(8 * h, kq);
           st_global_v4(y_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
           st_global_v4(y_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
         }
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
           tmem_st16(tAlo + c0 / 2, lo);
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const uint32_t o = mn128_offset(c0 + 8 * h, kq);
+            const uint32_t o = act_offset(c0 + 8 * h, kq);
             st_global_v4(y_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
             st_global_v4(y_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
           }
@@ -690,7 +697,7 @@ __global__ void __launch_bounds__(kThreadsWgrad, 1) mlp_wgrad_kernel(const __gri
   // "ones" operand [16 ch x 64 px], MN-major: channel 0 = 1.0 (bf16), channels 1..15 = 0 -> bias column sums
   for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0u;
   __syncthreads();
-  if (threadIdx.x < 64) *reinterpret_cast<uint16_t*>(ones + mn128_offset(0, threadIdx.x)) = (uint16_t)0x3F80u;
+  if (threadIdx.x < 64) *reinterpret_cast<uint16_t*>(ones + act_offset(0, threadIdx.x)) = (uint16_t)0x3F80u;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -724,13 +731,13 @@ __global__ void __launch_bounds__(kThreadsWgrad, 1) mlp_wgrad_kernel(const __gri
         tc_fence_after();
         const uint32_t sa_hi = smem_u32(stage[s]), sa_lo = sa_hi + 16384, sb_hi = sa_hi + 32768, sb_lo = sa_hi + 65536;
         for (int ks = 0; ks < 4; ++ks) {   // 16 pixels (K rows of 128 B) per MMA
-          const uint64_t ah = make_sdesc_mn_sw128(sa_hi + ks * 2048, 8192), al = make_sdesc_mn_sw128(sa_lo + ks * 2048, 8192);
-          const uint64_t bh = make_sdesc_mn_sw128(sb_hi + ks * 2048, 8192), bl = make_sdesc_mn_sw128(sb_lo + ks * 2048, 8192);
+          const uint64_t ah = act_desc(sa_hi, ks), al = act_desc(sa_lo, ks);
+          const uint64_t bh = act_desc(sb_hi, ks), bl = act_desc(sb_lo, ks);
           umma_ss(tmem + 0, ah, bh, idesc, accum);
           umma_ss(tmem + 0, al, bh, idesc, 1);
           umma_ss(tmem + 0, ah, bl, idesc, 1);
           if (J.bias_out) {
-            const uint64_t od = make_sdesc_mn_sw128(so + ks * 2048, 8192);
+            const uint64_t od = act_desc(so, ks);
             umma_ss(tmem + 256, ah, od, idesc_b, accum);
             umma_ss(tmem + 256, al, od, idesc_b, 1);
           }

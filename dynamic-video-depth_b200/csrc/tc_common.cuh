@@ -104,6 +104,24 @@ __device__ __forceinline__ uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint
   return d;
 }
 
+// MN-major operand WITHOUT swizzle ("interleave"): 8x8-element core matrices of 128 contiguous bytes
+// (8 K-rows of 16 bytes = 8 MN elements each); K-groups of 8 rows LBO = 128 bytes apart, MN-groups of 8 elements
+// SBO bytes apart. Element (mn, k) lives at (mn/8)*SBO + (k/8)*128 + (k%8)*16 + (mn%8)*2, so 32 threads that own
+// 32 consecutive K indices (pixels) write 512 contiguous bytes per 16-byte store. K advance of 16 rows = +256 bytes.
+__device__ __forceinline__ uint64_t make_sdesc_mn_interleave(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;        // LBO: next group of 8 K rows
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // SBO: next group of 8 MN elements
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)0 << 61;                              // SWIZZLE_NONE
+  return d;
+}
+// byte offset of element (mn, k) in a [rows x 64 k] interleaved MN-major block (SBO = 1024)
+__host__ __device__ __forceinline__ uint32_t il_offset(uint32_t mn, uint32_t k) {
+  return (mn >> 3) * 1024u + k * 16u + (mn & 7u) * 2u;
+}
+
 // Instruction descriptor for kind::f16: A,B = bf16, D = fp32. a_mn / b_mn: operand is MN-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn = false, bool b_mn = false) {
   return (1u << 4)                    // c_format = F32

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(160, 1) umma_selftest_kernel(const float* __re
   const int nchunk = K / 64;
   // smem carve-up: per chunk: A_hi (16 KB) A_lo (16 KB) B_hi (N*128) B_lo (N*128)
   // K-major blocks: rows x 128 B; MN-major blocks: ceil(rows/64) atoms of 8 KB
-  const uint32_t a_bytes = 128 * 128, b_bytes = (mode == 2) ? (uint32_t)((N + 63) / 64) * 8192u : (uint32_t)N * 128;
+  const uint32_t a_bytes = 128 * 128, b_bytes = (mode == 2) ? (uint32_t)((N + 63) / 64) * 8192u : (uint32_t)N * 128;   // mode 3: N/8 * 1024 = N * 128
   uint8_t* sA_hi = smem;
   uint8_t* sA_lo = sA_hi + nchunk * a_bytes;
   uint8_t* sB_hi = sA_lo + nchunk * a_bytes;
@@ -33,13 +33,13 @@ __global__ void __launch_bounds__(160, 1) umma_selftest_kernel(const float* __re
     }
   }
   // fill shared-memory operand images (generic proxy writes)
-  if (mode == 2) {
-    // MN-major images: pairs of consecutive rows (MN index) at the same k
+  if (mode == 2 || mode == 3) {
+    // MN-major images (mode 2: 128B swizzle, mode 3: no-swizzle interleave): pairs of consecutive rows at the same k
     for (int i = threadIdx.x; i < 128 * K / 2; i += blockDim.x) {
       int row = (i % 64) * 2, k = i / 64;
       uint32_t hi, lo;
       split2(A[row * K + k], A[(row + 1) * K + k], hi, lo);
-      uint32_t off = (k / 64) * a_bytes + mn128_offset(row, k % 64);
+      uint32_t off = (k / 64) * a_bytes + (mode == 2 ? mn128_offset(row, k % 64) : il_offset(row, k % 64));
       *reinterpret_cast<uint32_t*>(sA_hi + off) = hi;
       *reinterpret_cast<uint32_t*>(sA_lo + off) = lo;
     }
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(160, 1) umma_selftest_kernel(const float* __re
       int row = (i % (N / 2)) * 2, k = i / (N / 2);
       uint32_t hi, lo;
       split2(B[row * K + k], B[(row + 1) * K + k], hi, lo);
-      uint32_t off = (k / 64) * b_bytes + mn128_offset(row, k % 64);
+      uint32_t off = (k / 64) * b_bytes + (mode == 2 ? mn128_offset(row, k % 64) : il_offset(row, k % 64));
       *reinterpret_cast<uint32_t*>(sB_hi + off) = hi;
       *reinterpret_cast<uint32_t*>(sB_lo + off) = lo;
     }
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(160, 1) umma_selftest_kernel(const float* __re
   tc_fence_after();
 
   if (warp == 4 && lane == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, N, mode == 2, mode == 2);
+    const uint32_t idesc = make_idesc_bf16(128, N, mode >= 2, mode >= 2);
     uint32_t acc = 0;
     for (int p = 0; p < passes; ++p) {
       // p = 0: hi*hi, 1: lo(A)*hi(B), 2: hi(A)*lo(B)
@@ -105,6 +105,13 @@ __global__ void __launch_bounds__(160, 1) umma_selftest_kernel(const float* __re
       const uint8_t* b_img = (p == 2) ? sB_lo : sB_hi;
       for (int kc = 0; kc < nchunk; ++kc) {
         for (int ks = 0; ks < 4; ++ks) {  // 16 bf16 = 32 bytes per MMA
+          if (mode == 3) {
+            uint64_t ad = make_sdesc_mn_interleave(smem_u32(a_img + kc * a_bytes) + ks * 256, 1024);
+            uint64_t bd3 = make_sdesc_mn_interleave(smem_u32(b_img + kc * b_bytes) + ks * 256, 1024);
+            umma_ss(tD, ad, bd3, idesc, acc);
+            acc = 1;
+            continue;
+          }
           if (mode == 2) {
             uint64_t ad = make_sdesc_mn_sw128(smem_u32(a_img + kc * a_bytes) + ks * 2048, 8192);
             uint64_t bd2 = make_sdesc_mn_sw128(smem_u32(b_img + kc * b_bytes) + ks * 2048, 8192);
@@ -154,7 +161,7 @@ extern "C" int dvd_selftest_umma(const float* A, const float* B, float* D, int K
   DVD_ARG_CHECK(A && B && D, "null pointer");
   DVD_ARG_CHECK(K == 64 || K == 128, "K must be 64 or 128");
   DVD_ARG_CHECK(N >= 16 && N <= 256 && N % 16 == 0, "N must be a multiple of 16 in [16,256]");
-  DVD_ARG_CHECK(mode >= 0 && mode <= 2, "mode 0 (SS), 1 (TS) or 2 (SS, MN-major operands)");
+  DVD_ARG_CHECK(mode >= 0 && mode <= 3, "mode 0 (SS), 1 (TS), 2 (SS, MN-major swizzled) or 3 (SS, MN-major interleaved)");
   DVD_ARG_CHECK(passes == 1 || passes == 3, "passes 1 or 3");
   size_t smem = (size_t)(K / 64) * 2 * (128 * 128 + (size_t)((N + 63) / 64) * 8192) + 1024;
   DVD_CUDA_CALL(cudaFuncSetAttribute(dvd::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -22,7 +22,7 @@ def run_selftest(K, N, mode, passes, seed=0):
     return float((D.double() - ref).abs().max() / ref.abs().max())
 
 
-@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('mode', [0, 1, 2, 3])
 @pytest.mark.parametrize('K,N', [(64, 256), (128, 256), (128, 16), (64, 64), (64, 144)])
 def test_umma_bf16x3_is_fp32_grade(K, N, mode):
     assert run_selftest(K, N, mode, 3) < 2e-5

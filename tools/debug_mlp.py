@@ -12,21 +12,14 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
 def decode_blocks(buf, off, rows, nq, npx):
-    """[plane hi | plane lo] of nq MN-major blocks (64 px each, 64-channel atoms of 8 KB) -> fp32 [rows, npx]"""
-    atoms = (rows + 63) // 64
-    blk = atoms * 8192
+    """[plane hi | plane lo] of nq interleaved MN-major blocks ([rows/8][64 px][8 ch], sf_mlp_layout.cuh:
+    kActInterleave = true) -> fp32 [rows, npx]"""
+    blk = (rows + 7) // 8 * 1024
     plane_bytes = nq * blk
     out = None
     for pl in range(2):
-        raw = buf[off + pl * plane_bytes: off + (pl + 1) * plane_bytes].view(torch.int16).reshape(nq, atoms, 8, 8, 8, 8)
-        # dims: [q, atom, kgroup, r, physchunk, e]; logical chunk c = phys ^ r ; px = kgroup*8 + r ; ch = atom*64 + c*8 + e
-        r = torch.arange(8).reshape(8, 1)
-        c = torch.arange(8).reshape(1, 8)
-        phys = (c ^ r).to(raw.device)
-        idx = phys.reshape(1, 1, 1, 8, 8, 1).expand(nq, atoms, 8, 8, 8, 8)
-        logical = torch.gather(raw, 4, idx)  # [q, atom, g, r, c, e]
-        vals = logical.view(torch.bfloat16).float()
-        vals = vals.permute(1, 4, 5, 0, 2, 3).reshape(atoms * 64, nq * 64)[:rows, :npx]
+        raw = buf[off + pl * plane_bytes: off + (pl + 1) * plane_bytes].view(torch.int16).reshape(nq, rows // 8, 64, 8)
+        vals = raw.view(torch.bfloat16).float().permute(1, 3, 0, 2).reshape(rows, nq * 64)[:, :npx]
         out = vals if out is None else out + vals
     return out
 
@@ -53,13 +46,13 @@ def main():
     xs_off, o = [], 0
     for l in range(6):
         xs_off.append(o)
-        o += 2 * nq * ((rows_x[l] + 63) // 64) * 8192
+        o += 2 * nq * ((rows_x[l] + 7) // 8) * 1024
     mask_off = o
     rows_dy = [256] * 5 + [16]
     dy_off, o = [], 0
     for l in range(6):
         dy_off.append(o)
-        o += 2 * nq * ((rows_dy[l] + 63) // 64) * 8192
+        o += 2 * nq * ((rows_dy[l] + 7) // 8) * 1024
     # fp64 reference with autograd, keeping intermediates
     p = P1.double().reshape(B, 3, -1).permute(1, 0, 2).reshape(3, npx).clone().requires_grad_()
     t = ts.double().reshape(B, 1, -1).permute(1, 0, 2).reshape(1, npx)

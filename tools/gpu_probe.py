@@ -8,7 +8,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = [(64, 256, 0, 1), (64, 256, 0, 3), (128, 256, 0, 3), (128, 16, 0, 3), (64, 64, 0, 3),
          (64, 256, 1, 1), (64, 256, 1, 3), (128, 256, 1, 3), (128, 16, 1, 3), (64, 64, 1, 3),
-         (64, 256, 2, 1), (64, 256, 2, 3), (128, 256, 2, 3), (128, 16, 2, 3), (64, 144, 2, 3)]
+         (64, 256, 2, 1), (64, 256, 2, 3), (128, 256, 2, 3), (128, 16, 2, 3), (64, 144, 2, 3),
+         (64, 256, 3, 3), (128, 256, 3, 3), (128, 16, 3, 3), (64, 144, 3, 3)]
 
 CODE = """
 import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)
