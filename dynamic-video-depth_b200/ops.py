@@ -409,6 +409,7 @@ class BnAct(torch.autograd.Function):
         _lib.check(lib.dvd_bn_act_fwd(_ptr(x), _ptr(r), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), float(eps), _ptr(y),
                                       N * H * W, C, int(relu), _stream()), 'dvd_bn_act_fwd')
         ctx.save_for_backward(x, y, gamma, mean, var)
+        ctx.beta = beta
         ctx.eps, ctx.relu, ctx.has_res = float(eps), bool(relu), res is not None
         return y
 
@@ -419,12 +420,23 @@ class BnAct(torch.autograd.Function):
         N, C, H, W = x.shape
         gx = torch.empty_like(x)
         gres = torch.empty_like(x) if ctx.has_res else None
-        gg = torch.zeros_like(gamma)
-        gb = torch.zeros_like(gamma)
+        beta = ctx.beta
+        # The per-channel sums are atomically ACCUMULATED by the kernel. When gamma/beta already own a .grad buffer
+        # (the flat gradient buffer of dvd_b200.flat.FlatParams, zeroed once per step) they are accumulated there
+        # directly and autograd gets None (= zero) for them: no fill, no extra add kernels.
+        direct = (gamma.requires_grad and beta.requires_grad and gamma.grad is not None and beta.grad is not None
+                  and gamma.grad.is_contiguous() and beta.grad.is_contiguous() and gamma.grad.dtype == torch.float32)
+        if direct:
+            gg, gb = gamma.grad, beta.grad
+        else:
+            ggb = torch.zeros(2, C, dtype=torch.float32, device=x.device)   # one fill for both per-channel sums
+            gg, gb = ggb[0], ggb[1]
         lib = _lib.load()
         LAUNCHES['n'] += 1
         _lib.check(lib.dvd_bn_act_bwd(_ptr(g), _ptr(x), _ptr(y), _ptr(gamma), _ptr(mean), _ptr(var), ctx.eps, _ptr(gx), _ptr(gres),
                                       _ptr(gg), _ptr(gb), N * H * W, C, int(ctx.relu), _stream()), 'dvd_bn_act_bwd')
+        if direct:
+            return gx, gres, None, None, None, None, None, None
         return gx, gres, gg, gb, None, None, None, None
 
 
