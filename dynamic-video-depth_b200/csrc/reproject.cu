@@ -566,6 +566,92 @@ __global__ void __launch_bounds__(kThreads) reproject_materialize_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// adjoint of reproject_materialize_kernel for ARBITRARY cotangents on its nine outputs (operator-level drop-in:
+// the mirrors of flow_by_depth / scene_flow_projection_slack stay differentiable for user-defined losses).
+struct MatGrads {
+  const float* global_p1; const float* sf_by_depth; const float* warped_global_p2; const float* warped_p2_camera_2;
+  const float* p1_camera_2; const float* dflow; const float* staticflow; const float* depth_image; const float* depth_warp;
+};
+__device__ __forceinline__ void ld3(const float* p, size_t o3, int HW, float& a, float& b, float& c) {
+  if (p) { a = p[o3]; b = p[o3 + HW]; c = p[o3 + 2 * (size_t)HW]; } else { a = b = c = 0.f; }
+}
+__global__ void __launch_bounds__(kThreads) reproject_materialize_bwd_kernel(
+    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
+    const float* __restrict__ sf, const float* __restrict__ poses, MatGrads G, float* __restrict__ g_d1,
+    float* __restrict__ g_d2, float* __restrict__ g_sf, int H, int W) {
+  __shared__ Pose ps;
+  const int b = blockIdx.y;
+  load_pose(ps, poses, b);
+  __syncthreads();
+  const int HW = H * W;
+  const float* d2img = depth_2 + (size_t)b * HW;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+    const int y = pix / W, xi = pix - y * W;
+    const float x = (float)xi, yf = (float)y;
+    const float d1 = depth_1[(size_t)b * HW + pix];
+    const float2 f = *reinterpret_cast<const float2*>(flow + ((size_t)b * HW + pix) * 2);
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    const size_t o3 = (size_t)b * 3 * HW + pix, o2 = (size_t)b * 2 * HW + pix, o1 = (size_t)b * HW + pix;
+    if (sf) { sx = sf[o3]; sy = sf[o3 + HW]; sz = sf[o3 + 2 * (size_t)HW]; }
+    Taps tp = make_taps(x + f.x, yf + f.y, H, W);
+    Px o, os;
+    forward_px<false>(ps, d2img, tp, x, yf, d1, sx, sy, sz, o);
+    float a0, a1, a2, b0, b1, b2;
+    // P1: + global_p1, - sf_by_depth ;  wP2: + sf_by_depth, + warped_global_p2
+    float gP0, gP1, gP2, gW0, gW1, gW2;
+    ld3(G.global_p1, o3, HW, gP0, gP1, gP2);
+    ld3(G.sf_by_depth, o3, HW, a0, a1, a2);
+    gP0 -= a0; gP1 -= a1; gP2 -= a2;
+    ld3(G.warped_global_p2, o3, HW, gW0, gW1, gW2);
+    gW0 += a0; gW1 += a1; gW2 += a2;
+    // wpc: + warped_p2_camera_2 + R2^T g_wP2
+    float gC0, gC1, gC2;
+    ld3(G.warped_p2_camera_2, o3, HW, gC0, gC1, gC2);
+    mtv(ps.R2, gW0, gW1, gW2, a0, a1, a2);
+    gC0 += a0; gC1 += a1; gC2 += a2;
+    // p12: + p1_camera_2 + K^T g_i12
+    float gp0, gp1, gp2;
+    ld3(G.p1_camera_2, o3, HW, gp0, gp1, gp2);
+    float gi0 = 0.f, gi1 = 0.f, gi2 = G.depth_image ? G.depth_image[o1] : 0.f;
+    if (G.dflow && o.zok) {
+      const float gu = G.dflow[o2], gv = G.dflow[o2 + HW];
+      gi0 += gu * o.rz; gi1 += gv * o.rz;
+      gi2 -= (gu * o.i12[0] + gv * o.i12[1]) * o.rz * o.rz;
+    }
+    mtv(ps.K, gi0, gi1, gi2, a0, a1, a2);
+    gp0 += a0; gp1 += a1; gp2 += a2;
+    mv(ps.R2, gp0, gp1, gp2, b0, b1, b2);        // g_(P1 + sf)
+    if (g_sf) { g_sf[o3] = b0; g_sf[o3 + HW] = b1; g_sf[o3 + 2 * (size_t)HW] = b2; }
+    gP0 += b0; gP1 += b1; gP2 += b2;
+    if (G.staticflow) {
+      forward_px<false>(ps, d2img, tp, x, yf, d1, 0.f, 0.f, 0.f, os);
+      if (os.zok) {
+        const float gu = G.staticflow[o2], gv = G.staticflow[o2 + HW];
+        const float s0 = gu * os.rz, s1 = gv * os.rz, s2 = -(gu * os.i12[0] + gv * os.i12[1]) * os.rz * os.rz;
+        mtv(ps.K, s0, s1, s2, a0, a1, a2);
+        mv(ps.R2, a0, a1, a2, b0, b1, b2);
+        gP0 += b0; gP1 += b1; gP2 += b2;
+      }
+    }
+    // P1 = d1 * (M1 c) + t1
+    float rx, ry, rz;
+    ray_of(ps.M1, x, yf, rx, ry, rz);
+    if (g_d1) g_d1[o1] = fmaf(gP2, rz, fmaf(gP1, ry, gP0 * rx));
+    if (g_d2) {
+      float hu, hv, h1;
+      mtv(ps.Kinv, gC0, gC1, gC2, hu, hv, h1);
+      if (G.depth_warp) h1 += G.depth_warp[o1];
+      float* gd2img = g_d2 + (size_t)b * HW;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float g = tp.w[k] * fmaf(hu, tp.ux[k & 1], fmaf(hv, tp.uy[k >> 1], h1));
+        if (g != 0.f) atomicAdd(gd2img + tp.idx[k], g);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs, int max_vec = 4) {
   bool al = true;
   for (const void* p : ptrs) al = al && (p == nullptr || aligned16(p));
@@ -718,5 +804,26 @@ extern "C" int dvd_reproject_materialize(const float* depth_1, const float* dept
                                                        warped_global_p2, warped_p2_camera_2, p1_camera_2, dflow_1_2,
                                                        staticflow_1_2, depth_image_1_2, depth_warp_1_2, H, W);
   DVD_CUDA_LAUNCH_CHECK("reproject_materialize");
+  return 0;
+}
+
+extern "C" int dvd_reproject_materialize_bwd(const float* depth_1, const float* depth_2, const float* flow_1_2,
+                                             const float* sf, const float* poses, const float* g_global_p1,
+                                             const float* g_sf_by_depth, const float* g_warped_global_p2,
+                                             const float* g_warped_p2_camera_2, const float* g_p1_camera_2,
+                                             const float* g_dflow_1_2, const float* g_staticflow_1_2,
+                                             const float* g_depth_image_1_2, const float* g_depth_warp_1_2,
+                                             float* g_depth_1, float* g_depth_2, float* g_sf, int B, int H, int W,
+                                             void* stream) {
+  if (int e = check_shape(B, H, W)) return e;
+  DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && poses, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_depth_2) DVD_CUDA_CALL(cudaMemsetAsync(g_depth_2, 0, (size_t)B * H * W * sizeof(float), st));
+  MatGrads G{g_global_p1, g_sf_by_depth, g_warped_global_p2, g_warped_p2_camera_2, g_p1_camera_2,
+             g_dflow_1_2, g_staticflow_1_2, g_depth_image_1_2, g_depth_warp_1_2};
+  dim3 g = grid_for(reproject_materialize_bwd_kernel, B, H * W);
+  reproject_materialize_bwd_kernel<<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, sf, poses, G, g_depth_1, g_depth_2,
+                                                         g_sf, H, W);
+  DVD_CUDA_LAUNCH_CHECK("reproject_materialize_bwd");
   return 0;
 }

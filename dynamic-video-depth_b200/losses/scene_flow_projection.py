@@ -4,9 +4,8 @@ result-dict keys / shapes / dtypes, dispatching to the fused CUDA kernels throug
 The training fast path does NOT go through these modules (Model uses ops.reproject_loss, which never
 materialises per-pixel tensors); they exist for the operator-level drop-in and for visualised batches.
 Outputs are returned in the reference's layouts ([B,H,W,1,3] / [B,H,W,2] / [B,1,H,W]) as views of the
-channel-planar kernel outputs. Gradients: `unproject_ptcld` is differentiable; the two projection
-modules return detached tensors (the differentiable route is ops.reproject_loss) — documented in
-INTEGRATION.md.
+channel-planar kernel outputs and are differentiable w.r.t. depth_1, depth_2 and the scene flow for any
+downstream loss (ops.ReprojectMaterialize -> dvd_reproject_materialize / dvd_reproject_materialize_bwd).
 """
 from torch import nn
 
@@ -44,9 +43,7 @@ class flow_by_depth(nn.Module):
 
     def forward(self, depth_1, depth_2, flow_1_2, R_1, R_2, R_1_T, R_2_T, t_1, t_2, K, K_inv):
         poses = ops.pack_poses(K, K_inv, R_1_T, R_2_T, t_1, t_2)
-        o = ops.reproject_materialize(depth_1.detach().contiguous(), depth_2.detach().contiguous(),
-                                      flow_1_2.contiguous(), None, poses,
-                                      keys=('global_p1', 'sf_by_depth', 'warped_global_p2', 'staticflow_1_2'))
+        o = ops.reproject_tensors(depth_1, depth_2, None, flow_1_2.contiguous(), poses)
         # with no scene flow the projected flow is the static one
         return {'dflow_1_2': _bhw2(o['staticflow_1_2']), 'sf_by_depth': _bhw13(o['sf_by_depth']),
                 'warped_global_p2': _bhw13(o['warped_global_p2']), 'global_p1': _bhw13(o['global_p1'])}
@@ -62,9 +59,8 @@ class scene_flow_projection_slack(nn.Module):
     def forward(self, depth_1, depth_2, flow_1_2, flow_2_1, R_1, R_2, R_1_T, R_2_T, t_1, t_2, K, K_inv,
                 sflow_1_2, sflow_2_1):
         poses = ops.pack_poses(K, K_inv, R_1_T, R_2_T, t_1, t_2)
-        sf = sflow_1_2.squeeze(3).permute(0, 3, 1, 2).detach().contiguous()   # [B,H,W,1,3] -> [B,3,H,W]
-        o = ops.reproject_materialize(depth_1.detach().contiguous(), depth_2.detach().contiguous(),
-                                      flow_1_2.contiguous(), sf, poses)
+        sf = sflow_1_2.squeeze(3).permute(0, 3, 1, 2).contiguous()   # [B,H,W,1,3] -> [B,3,H,W]
+        o = ops.reproject_tensors(depth_1, depth_2, sf, flow_1_2.contiguous(), poses)
         return {'dflow_1_2': _bhw2(o['dflow_1_2']), 'depth_image_1_2': o['depth_image_1_2'],
                 'depth_warp_1_2': o['depth_warp_1_2'], 'depth_1': depth_1, 'depth_2': depth_2,
                 'scenef_1_2': sflow_1_2, 'global_p1': _bhw13(o['global_p1']),

@@ -476,3 +476,45 @@ class Upsample2x(torch.autograd.Function):
 
 def upsample2x(x, align_corners):
     return Upsample2x.apply(x, bool(align_corners))
+
+
+# ================================================================================================
+# differentiable materialisation (operator-level drop-in of the two projection modules)
+
+_MAT_ALL = _MAT_KEYS3 + _MAT_KEYS2 + _MAT_KEYS1
+
+
+class ReprojectMaterialize(torch.autograd.Function):
+    """All nine per-pixel tensors of flow_by_depth / scene_flow_projection_slack (channel-planar), differentiable
+    w.r.t. depth_1, depth_2 and sf for arbitrary cotangents (dvd_reproject_materialize_bwd)."""
+
+    @staticmethod
+    def forward(ctx, depth_1, depth_2, sf, flow, poses):
+        depth_1, depth_2 = depth_1.contiguous(), depth_2.contiguous()
+        sf = sf.contiguous() if sf is not None else None
+        out = reproject_materialize(depth_1, depth_2, flow, sf, poses)
+        ctx.save_for_backward(depth_1, depth_2, sf if sf is not None else depth_1.new_empty(0), flow, poses)
+        ctx.has_sf = sf is not None
+        return tuple(out[k] for k in _MAT_ALL)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        depth_1, depth_2, sf, flow, poses = ctx.saved_tensors
+        sf = sf if ctx.has_sf else None
+        B, _, H, W = depth_1.shape
+        gs = [g.contiguous() if g is not None else None for g in grads]
+        g_d1 = torch.empty_like(depth_1) if ctx.needs_input_grad[0] else None
+        g_d2 = torch.empty_like(depth_2) if ctx.needs_input_grad[1] else None
+        g_sf = torch.empty(B, 3, H, W, dtype=torch.float32, device=depth_1.device) if (ctx.has_sf and ctx.needs_input_grad[2]) else None
+        lib = _lib.load()
+        LAUNCHES['n'] += 1
+        _lib.check(lib.dvd_reproject_materialize_bwd(_ptr(depth_1), _ptr(depth_2), _ptr(flow), _ptr(sf), _ptr(poses),
+                                                     *[_ptr(g) for g in gs], _ptr(g_d1), _ptr(g_d2), _ptr(g_sf), B, H, W,
+                                                     _stream()), 'dvd_reproject_materialize_bwd')
+        return g_d1, g_d2, g_sf, None, None
+
+
+def reproject_tensors(depth_1, depth_2, sf, flow, poses):
+    """dict of the nine differentiable per-pixel tensors."""
+    _chk_reproject(depth_1.contiguous(), depth_2.contiguous(), flow, None, sf.contiguous() if sf is not None else None, poses)
+    return dict(zip(_MAT_ALL, ReprojectMaterialize.apply(depth_1, depth_2, sf, flow, poses)))

@@ -88,6 +88,18 @@ int dvd_reproject_materialize(const float* depth_1, const float* depth_2, const 
                               float* staticflow_1_2, float* depth_image_1_2, float* depth_warp_1_2,
                               int B, int H, int W, void* stream);
 
+/* adjoint of dvd_reproject_materialize for arbitrary cotangents on its nine outputs (any may be NULL = zero):
+ * keeps the operator-level mirrors of flow_by_depth / scene_flow_projection_slack differentiable.
+ * g_depth_1, g_sf overwritten; g_depth_2 zero-filled then scatter-added; each may be NULL.            */
+int dvd_reproject_materialize_bwd(const float* depth_1, const float* depth_2, const float* flow_1_2,
+                                  const float* sf, const float* poses, const float* g_global_p1,
+                                  const float* g_sf_by_depth, const float* g_warped_global_p2,
+                                  const float* g_warped_p2_camera_2, const float* g_p1_camera_2,
+                                  const float* g_dflow_1_2, const float* g_staticflow_1_2,
+                                  const float* g_depth_image_1_2, const float* g_depth_warp_1_2,
+                                  float* g_depth_1, float* g_depth_2, float* g_sf, int B, int H, int W,
+                                  void* stream);
+
 /* self-test of the tcgen05 building blocks (one CTA): D[128,N] = A[128,K]·B[N,K]^T, fp32 row-major
  * in/out, K in {64,128}, N multiple of 16 <= 256; mode 0 = A from shared memory, 1 = A from tensor
  * memory; passes 1 = bf16, 3 = bf16x3 split (fp32-grade). Not on the hot path.                 */

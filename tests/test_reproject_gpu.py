@@ -152,3 +152,40 @@ def test_large_batch_properties():
     assert abs(s8[4].item() - 8 * s1[4].item()) <= 1e-6 * abs(8 * s1[4].item())
     assert rel_err(g8[3] * 8, g1[0]) < 1e-5
     assert rel_err(gd8[5] * 8, gd1[0]) < 1e-4   # atomics: summation order differs
+
+
+def test_operator_mirrors_are_differentiable_for_arbitrary_losses():
+    """A user-defined loss on the mirrors' result dicts back-propagates like the reference modules would
+    (oracle autograd, fp64) — dvd_reproject_materialize_bwd."""
+    from dvd_b200 import synthetic
+    from dvd_b200.losses import scene_flow_projection as sfp
+    from oracle import geometry
+    B, H, W = 2, 20, 28
+    batch = synthetic.make_batch([(2, 5), (9, 10)], H=H, W=W, seed=4, leading_dim=False, flow_sigma=3.0)
+    d1 = synthetic.make_depths(B, H, W, seed=1)
+    d2 = synthetic.make_depths(B, H, W, seed=2)
+    sf = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(7)) * 0.05
+    gen = torch.Generator().manual_seed(8)
+    keys = ['global_p1', 'sf_by_depth', 'warped_global_p2', 'warped_p2_camera_2', 'p1_camera_2', 'dflow_1_2',
+            'staticflow_1_2', 'depth_image_1_2', 'depth_warp_1_2']
+    b64 = {k: (v.double() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    d1o, d2o, sfo = (t.double().requires_grad_() for t in (d1, d2, sf))
+    ro = geometry.reproject(d1o, d2o, sfo, b64)
+    cots = {k: torch.randn(ro[k].shape, generator=gen) for k in keys}
+    sum((ro[k] * cots[k].double()).sum() for k in keys).backward()
+    b = _dev(batch)
+    pose = {k: b[k] for k in ('R_1', 'R_2', 'R_1_T', 'R_2_T', 't_1', 't_2', 'K', 'K_inv')}
+    d1g, d2g, sfg = (t.cuda().requires_grad_() for t in (d1, d2, sf))
+    sfl = sfg.permute(0, 2, 3, 1)[..., None, :]
+    r1 = sfp.flow_by_depth()(depth_1=d1g, depth_2=d2g, flow_1_2=b['flow_1_2'], **pose)
+    r2 = sfp.scene_flow_projection_slack()(depth_1=d1g, depth_2=d2g, flow_1_2=b['flow_1_2'], flow_2_1=b['flow_2_1'],
+                                           sflow_1_2=sfl, sflow_2_1=sfl, **pose)
+    cf = lambda x: x.squeeze(3).permute(0, 3, 1, 2)  # noqa: E731
+    mine = {'global_p1': cf(r2['global_p1']), 'sf_by_depth': cf(r1['sf_by_depth']), 'warped_global_p2': cf(r1['warped_global_p2']),
+            'warped_p2_camera_2': cf(r2['warped_p2_camera_2']), 'p1_camera_2': cf(r2['p1_camera_2']),
+            'dflow_1_2': r2['dflow_1_2'].permute(0, 3, 1, 2), 'staticflow_1_2': r2['staticflow_1_2'].permute(0, 3, 1, 2),
+            'depth_image_1_2': r2['depth_image_1_2'], 'depth_warp_1_2': r2['depth_warp_1_2']}
+    sum((mine[k] * cots[k].cuda()).sum() for k in keys).backward()
+    assert rel_err(d1g.grad, d1o.grad) < 2e-4
+    assert rel_err(d2g.grad, d2o.grad) < 2e-4
+    assert rel_err(sfg.grad, sfo.grad) < 2e-4
