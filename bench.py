@@ -234,9 +234,8 @@ def roofline_mlp(tflops_peak, peak_kind, pairs=2, n_eval=2):
     """tcgen05 scene-flow MLP kernels, CUDA events. Useful work = 593 408 FLOP per pixel and evaluation
      for the forward, the same again for dgrad and for wgrad; the bf16x3 split issues 3x as many
     tensor-core MACs (reported as `issued`)."""
-    import ctypes
     import torch
-    from dvd_b200 import _lib, ops
+    from dvd_b200 import ops
     from oracle import sf_mlp
     dev = torch.device('cuda', torch.cuda.current_device())
     layers = sf_mlp.init_layers(seed=1)

@@ -18,7 +18,6 @@ step runs:
   5 x .item()                            (:321-323)         one 8-float D2H per step
   2 x torch.optim.Adam over ~430 tensors (:212-213)         dvd_adam_flat on flat buffers (+ NCCL all-reduce)
 """
-import math
 from os import makedirs
 from os.path import join
 

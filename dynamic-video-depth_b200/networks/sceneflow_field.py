@@ -2,7 +2,6 @@
 tcgen05 kernels. Same ctor signature, same state-dict names (`convs.{0..5}.conv.{weight,bias}`), same
 `forward(x[B,3,H,W], t[B,1,H,W]) -> [B,3,H,W]` (raw network output, before `/ sf_mag_div`).
 """
-import torch
 from torch import nn
 
 from .blocks import Conv2dBlock, PeriodicEmbed

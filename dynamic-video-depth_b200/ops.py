@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import LossCfg
+from ._lib import LossCfg, MlpCfg
 
 
 # number of dvd_b200 kernel launches issued through this module (bench.py reports it as gpu_launches)
@@ -214,9 +214,6 @@ def reproject_loss(depth_1, depth_2, sf, flow, mask, poses, cfg, gscale=1.0):
 
 # ================================================================================================
 # scene-flow MLP (tcgen05 kernels)
-
-from ._lib import MlpCfg  # noqa: E402
-
 
 def make_mlp_cfg(n_freq_xyz=16, n_freq_t=16, time_dependent=True, sf_mag_div=100.0):
     """struct dvd_mlp_cfg; frequencies = torch.linspace(1, N+1, N) in fp32 exactly as

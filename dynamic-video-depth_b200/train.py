@@ -7,7 +7,6 @@ wrappers are discarded (train.py:284-287) — gradients really are mean-all-redu
 NCCL over NVLink), after ONE flat parameter broadcast from rank 0.
 """
 import os
-import sys
 
 import torch
 import torch.distributed as dist

@@ -31,7 +31,6 @@ def test_synthetic_dataset_has_the_reference_batch_keys():
 
 def test_model_rejects_cpu_and_unknown_variants():
     import pytest
-    import torch
     from dvd_b200 import synthetic
     from dvd_b200.models import get_model
     with pytest.raises(NotImplementedError):

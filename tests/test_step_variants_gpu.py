@@ -4,7 +4,6 @@ reference by tests/test_oracle_step.py): hourglass depth net, --weight_steps, --
 import pytest
 import torch
 
-from conftest import rel_err
 from test_oracle_step import frac_within
 
 pytestmark = pytest.mark.gpu
