@@ -171,6 +171,12 @@ class Model(NetInterface):
             self._world = dist.get_world_size()
             for o in self._optimizers:
                 o.materialize().flat.broadcast(src)
+            # BatchNorm running statistics are buffers, not parameters: the reference relies on every rank having
+            # loaded the same checkpoint (train.py:290-292 broadcasts parameters only); broadcast them as well.
+            for net in self._nets:
+                for buf in net.buffers():
+                    if buf.dtype.is_floating_point:
+                        dist.broadcast(buf, src)
             self.net_sceneflow._packed_version = None
 
     # ---- helpers ------------------------------------------------------------------------------------------
