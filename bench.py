@@ -191,7 +191,7 @@ def roofline_reproject(pairs, hbm_peak, peak_kind):
     d1, d2 = rep(synthetic.make_depths(1, H, W, seed=1)), rep(synthetic.make_depths(1, H, W, seed=2))
     sf = torch.randn(pairs, 3, H, W, device=dev) * 0.05
     cfg = ops.make_loss_cfg()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)   # 256 MB, flushed by READING it (clean L2 lines)
     px = pairs * H * W
     scal = ops.reproject_loss_fwd(d1, d2, flow, mask, sf, poses, cfg)
     P = ops.unproject_fwd(d1, poses, 1)
@@ -203,15 +203,20 @@ def roofline_reproject(pairs, hbm_peak, peak_kind):
     for name, fn, bpp in cases:
         for _ in range(3):
             fn()
-        ts = []
+        torch.cuda.synchronize()
+        # every iteration is enqueued behind a ~20 ms spin kernel before the one synchronisation, so the host side of
+        # the call (ctypes + output allocation, ~50 us) runs ahead of the GPU and the event pair brackets device work only
+        torch.cuda._sleep(40_000_000)
+        evs = []
         for _ in range(10):
-            flush.zero_()
+            flush_sink = flush.sum()   # read 256 MB: evicts L2 without leaving dirty lines behind
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
             b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b) * 1e-3)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) * 1e-3 for a, b in evs]
         t = sum(ts) / len(ts)
         out.append({'kernel': name, 'bytes_per_px': bpp, 'us': t * 1e6, 'achieved': px * bpp / t / 1e9,
                     'frac': px * bpp / t / 1e9 / hbm_peak})

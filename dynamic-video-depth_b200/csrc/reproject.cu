@@ -16,8 +16,10 @@
 // Algorithmic HBM bytes per pixel (fp32): fwd 32 (d1 4, d2 4, flow 8, mask 4, sf 12);
 // bwd 48 (the same 32 read + g_sf 12 + g_d2 4 written). See DESIGN.md for the full accounting.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <initializer_list>
 #include <stdlib.h>
+#include <atomic>
 
 namespace dvd {
 
@@ -651,6 +653,628 @@ __global__ void __launch_bounds__(kThreads) reproject_materialize_bwd_kernel(
   }
 }
 
+// =============================================================================================
+// Packed-FP32 path of the fused loss kernels (sm_100: FFMA2 / FMUL2 / FADD2 process two fp32 lanes per issue slot).
+//
+// The scalar kernels above are bound by the FP32 issue rate, not by HBM (profiles/r1_ncu_reproject_*_v3.json:
+// ~218 / ~340 warp instructions per pixel forward / backward, issue slots 63 % busy at 27 % of DRAM peak). Here each
+// thread owns PAIRS of x-adjacent pixels and every matrix-vector product of the chain runs on float2 operands, the
+// pose entries entering as broadcast scalar operands straight from the constant bank (no shared-memory loads, no
+// register copies). Pose-derived matrices are prepared once per call by pose_prep_kernel and copied into a
+// __constant__ slot with a device-to-device cudaMemcpyToSymbolAsync on the caller's stream (no host round trip).
+struct __align__(16) PoseC {
+  float Kinv[9];   //  0
+  float K[9];      //  9
+  float R2[9];     // 18
+  float nM1[9];    // 27  -(R1 Kinv)                 -(P1 - t1) = d1 * (nM1 c)
+  float A[9];      // 36  R2^T R1 Kinv               p12 = d1 * (A c) + cv + R2^T sf
+  float cv[3];     // 45  R2^T (t1 - t2)
+  float t21[3];    // 48  t2 - t1                    warped_global_p2 - P1 = R2 wpc + t21 + d1 * (nM1 c)
+  float pad[13];
+};
+static_assert(sizeof(PoseC) == 256, "PoseC layout");
+constexpr int kPoseSlots = 3;    // rotating slots: calls in flight on different streams do not share a slot
+constexpr int kPosePairs = 64;   // pairs per launch (larger batches are processed in chunks)
+__constant__ PoseC c_pose[kPoseSlots][kPosePairs];
+__device__ PoseC g_pose_stage[kPoseSlots][kPosePairs];
+
+__global__ void pose_prep_kernel(const float* __restrict__ poses, int B, int slot) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* p = poses + (size_t)b * DVD_POSE_STRIDE;
+  float Kinv[9], R1[9], R2[9], M1[9], t1[3], t2[3];
+  PoseC& o = g_pose_stage[slot][b];
+  for (int i = 0; i < 9; ++i) {
+    Kinv[i] = p[i]; R1[i] = p[18 + i]; R2[i] = p[27 + i];
+    o.Kinv[i] = Kinv[i]; o.K[i] = p[9 + i]; o.R2[i] = R2[i];
+  }
+  for (int i = 0; i < 3; ++i) { t1[i] = p[36 + i]; t2[i] = p[39 + i]; }
+  mm3(R1, Kinv, M1, false);
+  mm3(R2, M1, o.A, true);
+  for (int i = 0; i < 9; ++i) o.nM1[i] = -M1[i];
+  const float dx = t1[0] - t2[0], dy = t1[1] - t2[1], dz = t1[2] - t2[2];
+  for (int i = 0; i < 3; ++i) {
+    o.cv[i] = fmaf(R2[6 + i], dz, fmaf(R2[3 + i], dy, R2[i] * dx));
+    o.t21[i] = t2[i] - t1[i];
+  }
+}
+
+__device__ __forceinline__ float2 F2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+// a - b as one FFMA2 (b * -1 + a)
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, F2(-1.0f), a); }
+// M * v  /  M^T * v  with broadcast matrix entries
+__device__ __forceinline__ void mv2(const float* M, float2 x, float2 y, float2 z, float2& ox, float2& oy, float2& oz) {
+  ox = fma2(F2(M[2]), z, fma2(F2(M[1]), y, mul2(F2(M[0]), x)));
+  oy = fma2(F2(M[5]), z, fma2(F2(M[4]), y, mul2(F2(M[3]), x)));
+  oz = fma2(F2(M[8]), z, fma2(F2(M[7]), y, mul2(F2(M[6]), x)));
+}
+__device__ __forceinline__ void mtv2(const float* M, float2 x, float2 y, float2 z, float2& ox, float2& oy, float2& oz) {
+  ox = fma2(F2(M[6]), z, fma2(F2(M[3]), y, mul2(F2(M[0]), x)));
+  oy = fma2(F2(M[7]), z, fma2(F2(M[4]), y, mul2(F2(M[1]), x)));
+  oz = fma2(F2(M[8]), z, fma2(F2(M[5]), y, mul2(F2(M[2]), x)));
+}
+
+// forward chain of one pixel pair
+struct PairOut {
+  int i00[2], sx1[2], sy1[2];   // nw tap index; element offsets to the ne / sw taps (0 where clamped by the border)
+  float2 w[4];            // bilinear weights; a tap clamped by the border has weight exactly 0
+  float2 x0f, y0f;        // tap origin (the ne / sw / se taps sit at +1 wherever their weight is non-zero)
+  float2 wpc[3], p12[3], i12[3], rz;
+  float2 ex, ey;          // dflow_1_2 - flow_1_2 (zero flow substituted where the projection is rejected)
+  float2 e[3];            // warped_global_p2 - P1 - sf            (kWorld only)
+  bool zok[2];
+};
+
+template <bool kWorld>
+__device__ __forceinline__ void pair_forward(const PoseC& ps, const float* __restrict__ d2img, int H, int W, float2 nx,
+                                             float nyf, float2 fx, float2 fy, float2 d1, float2 sx, float2 sy, float2 sz,
+                                             const float (&rn)[3], const float (&ra)[3], PairOut& o) {
+  const float hw = (float)(W - 1), hh = (float)(H - 1);
+  const float2 nqx = fma2(fx, F2(-1.0f), nx);        // -(x + flow_x)
+  const float2 nqy = fma2(fy, F2(-1.0f), F2(nyf));   // -(y + flow_y)
+  float ixs[2], iys[2], xfs[2], yfs[2];
+  const float nq[2][2] = {{nqx.x, nqy.x}, {nqx.y, nqy.y}};
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    ixs[j] = fminf(hw, fmaxf(-nq[j][0], 0.0f));
+    iys[j] = fminf(hh, fmaxf(-nq[j][1], 0.0f));
+    xfs[j] = floorf(ixs[j]);
+    yfs[j] = floorf(iys[j]);
+    const int xi = (int)xfs[j], yi = (int)yfs[j];
+    o.i00[j] = yi * W + xi;
+    o.sx1[j] = xi < W - 1 ? 1 : 0;
+    o.sy1[j] = yi < H - 1 ? W : 0;
+  }
+  float2 dk[4];
+  {
+    // one 64-bit address per pixel, the other taps at small element offsets from it
+    const float* pa = d2img + o.i00[0];
+    const float* pb = d2img + o.i00[1];
+    dk[0] = make_float2(__ldg(pa), __ldg(pb));
+    dk[1] = make_float2(__ldg(pa + o.sx1[0]), __ldg(pb + o.sx1[1]));
+    dk[2] = make_float2(__ldg(pa + o.sy1[0]), __ldg(pb + o.sy1[1]));
+    dk[3] = make_float2(__ldg(pa + o.sy1[0] + o.sx1[0]), __ldg(pb + o.sy1[1] + o.sx1[1]));
+  }
+  // ---- arithmetic that does not depend on the gathered taps first: it runs while the gather is in flight ----
+  // p12 = d1 (A c) + cv + R2^T sf ; c = (x, y, 1): A c = A[:,0] x + (A[:,1] y + A[:,2]) = -A[:,0] nx + ra
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float2 ac = fma2(F2(-ps.A[3 * k]), nx, F2(ra[k]));
+    float2 t = fma2(d1, ac, F2(ps.cv[k]));
+    t = fma2(F2(ps.R2[k]), sx, t);
+    t = fma2(F2(ps.R2[3 + k]), sy, t);
+    o.p12[k] = fma2(F2(ps.R2[6 + k]), sz, t);
+  }
+  mv2(ps.K, o.p12[0], o.p12[1], o.p12[2], o.i12[0], o.i12[1], o.i12[2]);
+  const float2 zz = add2(o.i12[2], F2(1e-8f));
+  o.rz = make_float2(rcp_fast(zz.x), rcp_fast(zz.y));
+  o.zok[0] = !(o.i12[2].x < 1e-3f);
+  o.zok[1] = !(o.i12[2].y < 1e-3f);
+  // dflow - flow = i12.xy * rz - (c.xy + flow)
+  const float2 ex = fma2(o.i12[0], o.rz, nqx), ey = fma2(o.i12[1], o.rz, nqy);
+  o.ex = make_float2(o.zok[0] ? ex.x : -fx.x, o.zok[1] ? ex.y : -fx.y);
+  o.ey = make_float2(o.zok[0] ? ey.x : -fy.x, o.zok[1] ? ey.y : -fy.y);
+  o.x0f = make_float2(xfs[0], xfs[1]);
+  o.y0f = make_float2(yfs[0], yfs[1]);
+  // clamped coordinate == W-1 (H-1) implies a zero fractional part, so the clamped taps need no explicit masking
+  const float2 wx1 = sub2(make_float2(ixs[0], ixs[1]), o.x0f), wy1 = sub2(make_float2(iys[0], iys[1]), o.y0f);
+  const float2 wx0 = fma2(wx1, F2(-1.0f), F2(1.0f)), wy0 = fma2(wy1, F2(-1.0f), F2(1.0f));
+  o.w[0] = mul2(wx0, wy0); o.w[1] = mul2(wx1, wy0); o.w[2] = mul2(wx0, wy1); o.w[3] = mul2(wx1, wy1);
+  float2 et[3];
+  if (kWorld) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float2 nr = fma2(F2(-ps.nM1[3 * k]), nx, F2(rn[k]));   // -(M1 c)_k
+      et[k] = sub2(fma2(d1, nr, F2(ps.t21[k])), k == 0 ? sx : (k == 1 ? sy : sz));
+    }
+  }
+  // ---- gathered taps ----
+  // wpc = sum_k w_k d2_k Kinv (u_k, v_k, 1) = Kinv (su, sv, s1), u_k = x0f (+1), v_k = y0f (+1)
+  const float2 wd0 = mul2(o.w[0], dk[0]), wd1 = mul2(o.w[1], dk[1]), wd2 = mul2(o.w[2], dk[2]), wd3 = mul2(o.w[3], dk[3]);
+  const float2 eb = add2(wd1, wd3), sb = add2(wd2, wd3);
+  const float2 s1 = add2(add2(wd0, wd1), sb);
+  const float2 su = fma2(o.x0f, s1, eb), sv = fma2(o.y0f, s1, sb);
+  mv2(ps.Kinv, su, sv, s1, o.wpc[0], o.wpc[1], o.wpc[2]);
+  if (kWorld) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float2 t = fma2(F2(ps.R2[3 * k]), o.wpc[0], et[k]);
+      t = fma2(F2(ps.R2[3 * k + 1]), o.wpc[1], t);
+      o.e[k] = fma2(F2(ps.R2[3 * k + 2]), o.wpc[2], t);
+    }
+  }
+}
+
+__device__ __forceinline__ float mask1(const dvd_loss_cfg& c, float m2, float d1, float wz) {
+  return (!c.midas || (d1 < 100.0f && wz < 100.0f)) ? m2 : 0.0f;
+}
+
+// fused forward, 4 pixels (two pairs) per thread
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) reproject_loss_fwd_f2_kernel(
+    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
+    const float* __restrict__ mask_2, const float* __restrict__ sf, dvd_loss_cfg cfg, float* __restrict__ partials,
+    int H, int W, int slot, int b0, int slots_per_pair) {
+  __shared__ float red[kThreads / 32][4];
+  const PoseC& ps = c_pose[slot][blockIdx.y];
+  const int b = b0 + blockIdx.y;
+  const int HW = H * W, items = HW / 4, Wv = W / 4;
+  const float* d2img = depth_2 + (size_t)b * HW;
+  float2 a_flow = F2(0.f), a_disp = F2(0.f), a_sf = F2(0.f), a_m = F2(0.f);
+  const int stride = gridDim.x * blockDim.x, sdy = stride / Wv, sdx = stride - sdy * Wv;
+  int it = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = it / Wv, xv = it - y * Wv;
+  for (; it < items; it += stride, y += sdy, xv += sdx) {
+    if (xv >= Wv) { xv -= Wv; ++y; }
+    const int x0 = xv * 4;
+    const size_t pix = (size_t)y * W + x0;
+    const float4 d1 = ldg_stream4(depth_1 + (size_t)b * HW + pix);
+    const float4 m2 = ldg_stream4(mask_2 + (size_t)b * HW + pix);
+    const float* sfp = sf + (size_t)b * 3 * HW + pix;
+    const float4 sx = ldg_stream4(sfp), sy = ldg_stream4(sfp + HW), sz = ldg_stream4(sfp + 2 * (size_t)HW);
+    const float* fp = flow + ((size_t)b * HW + pix) * 2;
+    const float4 fa = ldg_stream4(fp), fb = ldg_stream4(fp + 4);
+    const float yf = (float)y;
+    float rn[3], ra[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      rn[k] = fmaf(ps.nM1[3 * k + 1], yf, ps.nM1[3 * k + 2]);
+      ra[k] = fmaf(ps.A[3 * k + 1], yf, ps.A[3 * k + 2]);
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float xf = (float)(x0 + 2 * p);
+      const float2 nx = make_float2(-xf, -xf - 1.0f);
+      const float2 fx = p == 0 ? make_float2(fa.x, fa.z) : make_float2(fb.x, fb.z);
+      const float2 fy = p == 0 ? make_float2(fa.y, fa.w) : make_float2(fb.y, fb.w);
+      const float2 dd = p == 0 ? make_float2(d1.x, d1.y) : make_float2(d1.z, d1.w);
+      const float2 mm = p == 0 ? make_float2(m2.x, m2.y) : make_float2(m2.z, m2.w);
+      const float2 px = p == 0 ? make_float2(sx.x, sx.y) : make_float2(sx.z, sx.w);
+      const float2 py = p == 0 ? make_float2(sy.x, sy.y) : make_float2(sy.z, sy.w);
+      const float2 pz = p == 0 ? make_float2(sz.x, sz.y) : make_float2(sz.z, sz.w);
+      PairOut o;
+      pair_forward<true>(ps, d2img, H, W, nx, -yf, fx, fy, dd, px, py, pz, rn, ra, o);
+      const float2 m = make_float2(mask1(cfg, mm.x, dd.x, o.wpc[2].x), mask1(cfg, mm.y, dd.y, o.wpc[2].y));
+      float2 fl, dl, sl;
+      if (cfg.warm) fl = fma2(o.ex, o.ex, mul2(o.ey, o.ey));
+      else fl = make_float2(fabsf(o.ex.x) + fabsf(o.ey.x), fabsf(o.ex.y) + fabsf(o.ey.y));
+      dl = make_float2(disp_term(cfg, o.p12[2].x, o.wpc[2].x), disp_term(cfg, o.p12[2].y, o.wpc[2].y));
+      sl = make_float2(fabsf(o.e[0].x) + fabsf(o.e[1].x) + fabsf(o.e[2].x), fabsf(o.e[0].y) + fabsf(o.e[1].y) + fabsf(o.e[2].y));
+      a_flow = fma2(m, fl, a_flow);
+      a_disp = fma2(m, dl, a_disp);
+      a_sf = fma2(m, sl, a_sf);
+      a_m = add2(a_m, m);
+    }
+  }
+  float s_flow = warp_sum(a_flow.x + a_flow.y), s_disp = warp_sum(a_disp.x + a_disp.y);
+  float s_sf = warp_sum(a_sf.x + a_sf.y), s_m = warp_sum(a_m.x + a_m.y);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[wid][0] = s_flow; red[wid][1] = s_disp; red[wid][2] = s_sf; red[wid][3] = s_m; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) a += red[w][threadIdx.x];
+    partials[((size_t)b * slots_per_pair + blockIdx.x) * 4 + threadIdx.x] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged variant: the five streamed inputs (28 of the 32 bytes per pixel) travel global -> shared memory as 1-D bulk
+// async copies issued by a producer warp into a ring of kRStages tiles, completion on mbarriers; the 256 consumer threads
+// only see shared-memory latency for them, and the bytes in flight per SM (2 CTAs x kRStages x 28 KB) no longer depend
+// on occupancy or on how the compiler schedules the loads. Only the bilinear gather of depth_2 is a global load.
+// bring [p, p + bytes) into L2 (hint only; bytes multiple of 16)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// The gathered image depth_2 of the whole chunk (nb x HW floats, 22 MB at 64 pairs of 384x224) fits in L2 many times
+// over: every CTA prefetches an equal slice up front so that the data-dependent bilinear taps find their sectors in L2
+// instead of paying a second DRAM round trip behind the streamed loads.
+__device__ __forceinline__ void prefetch_gather_image(const float* d2chunk, size_t floats) {
+  const size_t bytes = floats * 4, per = ((bytes + gridDim.x - 1) / gridDim.x + 15) & ~(size_t)15;
+  size_t lo = (size_t)blockIdx.x * per, hi = lo + per < bytes ? lo + per : bytes;
+  const char* base = reinterpret_cast<const char*>(d2chunk);
+  for (size_t o = lo + (size_t)(threadIdx.x & 31) * 4096; o < hi; o += 32 * 4096) {
+    const size_t n = hi - o < 4096 ? hi - o : 4096;
+    l2_prefetch_bulk(base + o, (uint32_t)(n & ~(size_t)15));
+  }
+}
+
+template <int NP> struct StagedCfg {
+  static constexpr int VEC = 2 * NP;                 // pixels per consumer thread and tile
+  static constexpr int TILE = kThreads * VEC;        // pixels per stage
+  static constexpr int FLOATS = TILE * 7;            // d1, mask, sf.x, sf.y, sf.z, flow (2 floats per pixel)
+};
+
+// stream one tile (pixels [p0, p0 + n) of pair b) into a stage
+template <int TILE>
+__device__ __forceinline__ void produce_tile(float* dst, uint64_t* bar, const float* depth_1, const float* mask_2,
+                                             const float* sf, const float* flow, size_t b, int HW, int p0) {
+  using namespace tc;
+  const uint32_t n4 = (uint32_t)min(TILE, HW - p0) * 4u;
+  mbar_arrive_expect_tx(bar, n4 * 7u);
+  bulk_g2s(dst, depth_1 + b * HW + p0, n4, bar);
+  bulk_g2s(dst + TILE, mask_2 + b * HW + p0, n4, bar);
+  bulk_g2s(dst + 2 * TILE, sf + (b * 3 + 0) * HW + p0, n4, bar);
+  bulk_g2s(dst + 3 * TILE, sf + (b * 3 + 1) * HW + p0, n4, bar);
+  bulk_g2s(dst + 4 * TILE, sf + (b * 3 + 2) * HW + p0, n4, bar);
+  bulk_g2s(dst + 5 * TILE, flow + (b * HW + p0) * 2, n4 * 2u, bar);
+}
+// a consumer thread's VEC pixels of a stage -> registers
+template <int NP>
+__device__ __forceinline__ void consume_tile(const float* src, int tv, float (&d1)[2 * NP], float (&m2)[2 * NP],
+                                             float (&sx)[2 * NP], float (&sy)[2 * NP], float (&sz)[2 * NP],
+                                             float (&fx)[2 * NP], float (&fy)[2 * NP]) {
+  constexpr int VEC = 2 * NP, TILE = StagedCfg<NP>::TILE;
+  src += tv;
+  if (VEC == 2) {
+    const float2 a = *reinterpret_cast<const float2*>(src), bq = *reinterpret_cast<const float2*>(src + TILE);
+    const float2 c = *reinterpret_cast<const float2*>(src + 2 * TILE), d = *reinterpret_cast<const float2*>(src + 3 * TILE);
+    const float2 e = *reinterpret_cast<const float2*>(src + 4 * TILE);
+    const float4 f = *reinterpret_cast<const float4*>(src + 5 * TILE + tv);
+    d1[0] = a.x; d1[1] = a.y; m2[0] = bq.x; m2[1] = bq.y; sx[0] = c.x; sx[1] = c.y; sy[0] = d.x; sy[1] = d.y;
+    sz[0] = e.x; sz[1] = e.y; fx[0] = f.x; fy[0] = f.y; fx[1] = f.z; fy[1] = f.w;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(src), bq = *reinterpret_cast<const float4*>(src + TILE);
+    const float4 c = *reinterpret_cast<const float4*>(src + 2 * TILE), d = *reinterpret_cast<const float4*>(src + 3 * TILE);
+    const float4 e = *reinterpret_cast<const float4*>(src + 4 * TILE);
+    const float4 f = *reinterpret_cast<const float4*>(src + 5 * TILE + tv), g = *reinterpret_cast<const float4*>(src + 5 * TILE + tv + 4);
+    d1[0] = a.x; d1[1] = a.y; d1[2 % VEC] = a.z; d1[3 % VEC] = a.w;
+    m2[0] = bq.x; m2[1] = bq.y; m2[2 % VEC] = bq.z; m2[3 % VEC] = bq.w;
+    sx[0] = c.x; sx[1] = c.y; sx[2 % VEC] = c.z; sx[3 % VEC] = c.w;
+    sy[0] = d.x; sy[1] = d.y; sy[2 % VEC] = d.z; sy[3 % VEC] = d.w;
+    sz[0] = e.x; sz[1] = e.y; sz[2 % VEC] = e.z; sz[3 % VEC] = e.w;
+    fx[0] = f.x; fy[0] = f.y; fx[1] = f.z; fy[1] = f.w; fx[2 % VEC] = g.x; fy[2 % VEC] = g.y; fx[3 % VEC] = g.z; fy[3 % VEC] = g.w;
+  }
+}
+
+// NP pixel pairs per consumer thread, STAGES-deep ring, MINB co-resident CTAs per SM
+template <int NP, int STAGES, int MINB, bool kDry>
+__global__ void __launch_bounds__(kThreads + 32, MINB) reproject_loss_fwd_staged_kernel(
+    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
+    const float* __restrict__ mask_2, const float* __restrict__ sf, dvd_loss_cfg cfg, float* __restrict__ partials,
+    int H, int W, int slot, int b0, int nb, int tiles_per_pair) {
+  using namespace tc;
+  constexpr int VEC = 2 * NP, TILE = StagedCfg<NP>::TILE, FLOATS = StagedCfg<NP>::FLOATS;
+  extern __shared__ __align__(128) float stage_mem[];
+  __shared__ uint64_t full[STAGES], empty[STAGES];
+  __shared__ float red[kThreads / 32][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = H * W, ntiles = nb * tiles_per_pair;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kThreads / 32); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == kThreads / 32) {
+    // ===== producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int bl = tile / tiles_per_pair, t = tile - bl * tiles_per_pair;
+        produce_tile<TILE>(stage_mem + (size_t)s * FLOATS, &full[s], depth_1, mask_2, sf, flow, (size_t)(b0 + bl), HW, t * TILE);
+      }
+    }
+    return;
+  }
+  // ===== consumers =====
+  float2 a_flow = F2(0.f), a_disp = F2(0.f), a_sf = F2(0.f), a_m = F2(0.f);
+  const int tv = threadIdx.x * VEC;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+    mbar_wait(&full[s], ph);
+    float d1[VEC], m2[VEC], sx[VEC], sy[VEC], sz[VEC], fx[VEC], fy[VEC];
+    consume_tile<NP>(stage_mem + (size_t)s * FLOATS, tv, d1, m2, sx, sy, sz, fx, fy);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);     // values are in registers: hand the stage back
+    const int bl = tile / tiles_per_pair, t = tile - bl * tiles_per_pair;
+    const int p = t * TILE + tv;
+    if (p >= HW) continue;
+    if (kDry) {   // memory-system probe (DVD_REPROJECT_DRY=1): stream the inputs, one gather tap, no chain arithmetic
+      const float g = __ldg(depth_2 + (size_t)(b0 + bl) * HW + p);
+      a_flow = add2(a_flow, make_float2(d1[0] + d1[1] + g, m2[0] + m2[1]));
+      a_sf = add2(a_sf, make_float2(sx[0] + sy[1] + sz[0], fx[0] + fy[1]));
+      if (VEC == 4) a_m = add2(a_m, make_float2(d1[VEC - 1] + m2[VEC - 1] + sx[VEC - 1] + sy[VEC - 2], sz[VEC - 1] + fx[VEC - 1] + fy[VEC - 2]));
+      continue;
+    }
+    const PoseC& ps = c_pose[slot][bl];
+    const float* d2img = depth_2 + (size_t)(b0 + bl) * HW;
+    const int y = p / W, x0 = p - y * W;
+    const float yf = (float)y;
+    float rn[3], ra[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      rn[k] = fmaf(ps.nM1[3 * k + 1], yf, ps.nM1[3 * k + 2]);
+      ra[k] = fmaf(ps.A[3 * k + 1], yf, ps.A[3 * k + 2]);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const int j = 2 * q;
+      const float xf = (float)(x0 + j);
+      const float2 nx = make_float2(-xf, -xf - 1.0f);
+      const float2 dd = make_float2(d1[j], d1[j + 1]);
+      PairOut o;
+      pair_forward<true>(ps, d2img, H, W, nx, -yf, make_float2(fx[j], fx[j + 1]), make_float2(fy[j], fy[j + 1]), dd,
+                         make_float2(sx[j], sx[j + 1]), make_float2(sy[j], sy[j + 1]), make_float2(sz[j], sz[j + 1]), rn, ra, o);
+      const float2 m = make_float2(mask1(cfg, m2[j], dd.x, o.wpc[2].x), mask1(cfg, m2[j + 1], dd.y, o.wpc[2].y));
+      float2 fl, dl, sl;
+      if (cfg.warm) fl = fma2(o.ex, o.ex, mul2(o.ey, o.ey));
+      else fl = make_float2(fabsf(o.ex.x) + fabsf(o.ey.x), fabsf(o.ex.y) + fabsf(o.ey.y));
+      dl = make_float2(disp_term(cfg, o.p12[2].x, o.wpc[2].x), disp_term(cfg, o.p12[2].y, o.wpc[2].y));
+      sl = make_float2(fabsf(o.e[0].x) + fabsf(o.e[1].x) + fabsf(o.e[2].x), fabsf(o.e[0].y) + fabsf(o.e[1].y) + fabsf(o.e[2].y));
+      a_flow = fma2(m, fl, a_flow);
+      a_disp = fma2(m, dl, a_disp);
+      a_sf = fma2(m, sl, a_sf);
+      a_m = add2(a_m, m);
+    }
+  }
+  float s_flow = warp_sum(a_flow.x + a_flow.y), s_disp = warp_sum(a_disp.x + a_disp.y);
+  float s_sf = warp_sum(a_sf.x + a_sf.y), s_m = warp_sum(a_m.x + a_m.y);
+  if (lane == 0) { red[warp][0] = s_flow; red[warp][1] = s_disp; red[warp][2] = s_sf; red[warp][3] = s_m; }
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");    // consumers only (the producer warp has exited)
+  if (threadIdx.x < 4) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) a += red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 4 + threadIdx.x] = a;
+  }
+}
+
+// c * sign(v) (0 at v == 0), lane-wise
+__device__ __forceinline__ float2 sgn_scale2(float2 v, float2 c) {
+  const unsigned sx = __float_as_uint(c.x) ^ (__float_as_uint(v.x) & 0x80000000u);   // one LOP3 per lane
+  const unsigned sy = __float_as_uint(c.y) ^ (__float_as_uint(v.y) & 0x80000000u);
+  return make_float2(v.x == 0.f ? 0.f : __uint_as_float(sx), v.y == 0.f ? 0.f : __uint_as_float(sy));
+}
+
+// backward of one pixel pair: returns g_(P1 + sf) and scatters g_depth_2
+__device__ __forceinline__ void pair_backward(const PoseC& ps, const dvd_loss_cfg& cfg, const float* __restrict__ d2img,
+                                              float* __restrict__ gd2img, int H, int W, float2 nx, float nyf, float2 fx,
+                                              float2 fy, float2 dd, float2 mm, float2 psx, float2 psy, float2 psz,
+                                              const float (&rn)[3], const float (&ra)[3], float cf, float cd, float2& gv0,
+                                              float2& gv1, float2& gv2) {
+      PairOut o;
+      if (cfg.second_is_disp) pair_forward<false>(ps, d2img, H, W, nx, nyf, fx, fy, dd, psx, psy, psz, rn, ra, o);
+      else                    pair_forward<true>(ps, d2img, H, W, nx, nyf, fx, fy, dd, psx, psy, psz, rn, ra, o);
+      const float2 m = make_float2(mask1(cfg, mm.x, dd.x, o.wpc[2].x), mask1(cfg, mm.y, dd.y, o.wpc[2].y));
+      // --- flow term -> g_i12 (zero where the projection was rejected)
+      const float2 mcf = make_float2(o.zok[0] ? m.x * cf : 0.f, o.zok[1] ? m.y * cf : 0.f);
+      float2 gux, guy;
+      if (cfg.warm) {
+        const float2 t2 = add2(mcf, mcf);
+        gux = mul2(t2, o.ex); guy = mul2(t2, o.ey);
+      } else {
+        gux = sgn_scale2(o.ex, mcf); guy = sgn_scale2(o.ey, mcf);
+      }
+      const float2 gi0 = mul2(gux, o.rz), gi1 = mul2(guy, o.rz);
+      const float2 tt = fma2(gux, o.i12[0], mul2(guy, o.i12[1]));
+      const float2 gi2 = mul2(mul2(tt, o.rz), mul2(o.rz, F2(-1.0f)));
+      float2 gp0, gp1, gp2;   // g_p12 = K^T g_i12
+      mtv2(ps.K, gi0, gi1, gi2, gp0, gp1, gp2);
+      float2 hu, hv, h1;      // Kinv^T g_warped_p2_camera_2
+      float2 ge0 = F2(0.f), ge1 = F2(0.f), ge2 = F2(0.f);
+      const float2 mc = mul2(m, F2(cd));
+      if (cfg.second_is_disp) {
+        const float2 za = o.p12[2], zb = o.wpc[2];
+        float2 gwc2;
+        if (cfg.disp_mode == 0) {
+          const float2 ra2 = make_float2(rcp_fast(fmaxf(za.x, 1e-3f)), rcp_fast(fmaxf(za.y, 1e-3f)));
+          const float2 rb2 = make_float2(rcp_fast(fmaxf(zb.x, 1e-3f)), rcp_fast(fmaxf(zb.y, 1e-3f)));
+          const float2 s = sgn_scale2(sub2(ra2, rb2), mul2(mc, F2(100.0f)));
+          const float2 sa = make_float2(za.x >= 1e-3f ? s.x : 0.f, za.y >= 1e-3f ? s.y : 0.f);
+          const float2 sb = make_float2(zb.x >= 1e-3f ? s.x : 0.f, zb.y >= 1e-3f ? s.y : 0.f);
+          gp2 = fma2(mul2(sa, ra2), mul2(ra2, F2(-1.0f)), gp2);
+          gwc2 = mul2(mul2(sb, rb2), rb2);
+        } else if (cfg.disp_mode == 1) {
+          float g2a[2], g2b[2];
+          const float zas[2] = {za.x, za.y}, zbs[2] = {zb.x, zb.y}, mcs[2] = {mc.x, mc.y};
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float a = fmaxf(zas[q], 1e-3f), bb = fmaxf(zbs[q], 1e-3f);
+            const float ra1 = rcp_fast(a), rb1 = rcp_fast(bb);
+            float ga, gb;
+            if (a >= bb) { ga = rb1; gb = -a * rb1 * rb1; }
+            else         { ga = -bb * ra1 * ra1; gb = ra1; }
+            g2a[q] = zas[q] >= 1e-3f ? ga * mcs[q] : 0.f;
+            g2b[q] = zbs[q] >= 1e-3f ? gb * mcs[q] : 0.f;
+          }
+          gp2 = add2(gp2, make_float2(g2a[0], g2a[1]));
+          gwc2 = make_float2(g2b[0], g2b[1]);
+        } else {
+          const float2 s = sgn_scale2(sub2(za, zb), mc);
+          gp2 = add2(gp2, s);
+          gwc2 = mul2(s, F2(-1.0f));
+        }
+        hu = mul2(F2(ps.Kinv[6]), gwc2); hv = mul2(F2(ps.Kinv[7]), gwc2); h1 = mul2(F2(ps.Kinv[8]), gwc2);
+      } else {
+        ge0 = sgn_scale2(o.e[0], mc); ge1 = sgn_scale2(o.e[1], mc); ge2 = sgn_scale2(o.e[2], mc);
+        // warped_global_p2 = R2 wpc + t2  =>  g_wpc = R2^T g_e
+        float2 a0, a1, a2;
+        mtv2(ps.R2, ge0, ge1, ge2, a0, a1, a2);
+        mtv2(ps.Kinv, a0, a1, a2, hu, hv, h1);
+      }
+      // g_(P1 + sf) = R2 g_p12 ; the sf term adds -g_e to both P1 and sf
+      mv2(ps.R2, gp0, gp1, gp2, gv0, gv1, gv2);
+      gv0 = sub2(gv0, ge0); gv1 = sub2(gv1, ge1); gv2 = sub2(gv2, ge2);
+      // scatter to depth_2: g_d2_k = w_k (hu u_k + hv v_k + h1), (u_k, v_k) = (x0f, y0f) (+1)
+      if (gd2img) {
+        const float2 base = fma2(hu, o.x0f, fma2(hv, o.y0f, h1));
+        const float2 bx = add2(base, hu);
+        const float2 g0 = mul2(o.w[0], base), g1 = mul2(o.w[1], bx);
+        const float2 g2 = mul2(o.w[2], add2(base, hv)), g3 = mul2(o.w[3], add2(bx, hv));
+        float* qa = gd2img + o.i00[0];
+        float* qb = gd2img + o.i00[1];
+        if (g0.x != 0.f) atomicAdd(qa, g0.x);
+        if (g1.x != 0.f) atomicAdd(qa + o.sx1[0], g1.x);
+        if (g2.x != 0.f) atomicAdd(qa + o.sy1[0], g2.x);
+        if (g3.x != 0.f) atomicAdd(qa + o.sy1[0] + o.sx1[0], g3.x);
+        if (g0.y != 0.f) atomicAdd(qb, g0.y);
+        if (g1.y != 0.f) atomicAdd(qb + o.sx1[1], g1.y);
+        if (g2.y != 0.f) atomicAdd(qb + o.sy1[1], g2.y);
+        if (g3.y != 0.f) atomicAdd(qb + o.sy1[1] + o.sx1[1], g3.y);
+      }
+}
+
+// fused backward, NP pixel pairs per thread: g_sf (== g_global_p1) and the scatter-add of g_depth_2
+template <int NP>
+__global__ void __launch_bounds__(kThreads) reproject_loss_bwd_f2_kernel(
+    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
+    const float* __restrict__ mask_2, const float* __restrict__ sf, dvd_loss_cfg cfg, const float* __restrict__ scalars,
+    float gscale, const float* __restrict__ gscale_dev, float* __restrict__ g_sf, float* __restrict__ g_d2, int H, int W,
+    int slot, int b0) {
+  constexpr int VEC = 2 * NP;
+  const PoseC& ps = c_pose[slot][blockIdx.y];
+  const int b = b0 + blockIdx.y;
+  const float gs = gscale * (gscale_dev ? __ldg(gscale_dev) : 1.0f);
+  const float cf = __ldg(scalars + DVD_S_CF) * gs;
+  const float cd = __ldg(scalars + DVD_S_CD) * gs;
+  const int HW = H * W, items = HW / VEC, Wv = W / VEC;
+  const float* d2img = depth_2 + (size_t)b * HW;
+  float* gd2img = g_d2 ? g_d2 + (size_t)b * HW : nullptr;
+  const int stride = gridDim.x * blockDim.x, sdy = stride / Wv, sdx = stride - sdy * Wv;
+  int it = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = it / Wv, xv = it - y * Wv;
+  for (; it < items; it += stride, y += sdy, xv += sdx) {
+    if (xv >= Wv) { xv -= Wv; ++y; }
+    const int x0 = xv * VEC;
+    const size_t pix = (size_t)y * W + x0;
+    float d1[VEC], m2[VEC], sx[VEC], sy[VEC], sz[VEC], fx[VEC], fy[VEC];
+    float ox[VEC], oy[VEC], oz[VEC];
+    load_vec<VEC>(depth_1 + (size_t)b * HW + pix, d1);
+    load_vec<VEC>(mask_2 + (size_t)b * HW + pix, m2);
+    const float* sfp = sf + (size_t)b * 3 * HW + pix;
+    load_vec<VEC>(sfp, sx);
+    load_vec<VEC>(sfp + HW, sy);
+    load_vec<VEC>(sfp + 2 * (size_t)HW, sz);
+    load_flow<VEC>(flow + ((size_t)b * HW + pix) * 2, fx, fy);
+    const float yf = (float)y;
+    float rn[3], ra[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      rn[k] = fmaf(ps.nM1[3 * k + 1], yf, ps.nM1[3 * k + 2]);
+      ra[k] = fmaf(ps.A[3 * k + 1], yf, ps.A[3 * k + 2]);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int j = 2 * p;
+      const float xf = (float)(x0 + j);
+      const float2 nx = make_float2(-xf, -xf - 1.0f);
+      const float2 dd = make_float2(d1[j], d1[j + 1]);
+      const float2 psx = make_float2(sx[j], sx[j + 1]), psy = make_float2(sy[j], sy[j + 1]), psz = make_float2(sz[j], sz[j + 1]);
+      float2 gv0, gv1, gv2;
+      pair_backward(ps, cfg, d2img, gd2img, H, W, nx, -yf, make_float2(fx[j], fx[j + 1]), make_float2(fy[j], fy[j + 1]), dd,
+                    make_float2(m2[j], m2[j + 1]), psx, psy, psz, rn, ra, cf, cd, gv0, gv1, gv2);
+      ox[j] = gv0.x; ox[j + 1] = gv0.y; oy[j] = gv1.x; oy[j + 1] = gv1.y; oz[j] = gv2.x; oz[j + 1] = gv2.y;
+    }
+    float* gsp = g_sf + (size_t)b * 3 * HW + pix;
+    store_vec<VEC>(gsp, ox);
+    store_vec<VEC>(gsp + HW, oy);
+    store_vec<VEC>(gsp + 2 * (size_t)HW, oz);
+  }
+}
+
+// staged backward (same producer / consumer ring as the staged forward), NP pixel pairs per consumer thread
+template <int NP, int STAGES, int MINB>
+__global__ void __launch_bounds__(kThreads + 32, MINB) reproject_loss_bwd_staged_kernel(
+    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
+    const float* __restrict__ mask_2, const float* __restrict__ sf, dvd_loss_cfg cfg, const float* __restrict__ scalars,
+    float gscale, const float* __restrict__ gscale_dev, float* __restrict__ g_sf, float* __restrict__ g_d2, int H, int W,
+    int slot, int b0, int nb, int tiles_per_pair) {
+  using namespace tc;
+  constexpr int VEC = 2 * NP, TILE = StagedCfg<NP>::TILE, FLOATS = StagedCfg<NP>::FLOATS;
+  extern __shared__ __align__(128) float stage_mem[];
+  __shared__ uint64_t full[STAGES], empty[STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HW = H * W, ntiles = nb * tiles_per_pair;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kThreads / 32); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == kThreads / 32) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int bl = tile / tiles_per_pair, t = tile - bl * tiles_per_pair;
+        produce_tile<TILE>(stage_mem + (size_t)s * FLOATS, &full[s], depth_1, mask_2, sf, flow, (size_t)(b0 + bl), HW, t * TILE);
+      }
+    }
+    return;
+  }
+  const float gs = gscale * (gscale_dev ? __ldg(gscale_dev) : 1.0f);
+  const float cf = __ldg(scalars + DVD_S_CF) * gs;
+  const float cd = __ldg(scalars + DVD_S_CD) * gs;
+  const int tv = threadIdx.x * VEC;
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+    mbar_wait(&full[s], ph);
+    float d1[VEC], m2[VEC], sx[VEC], sy[VEC], sz[VEC], fx[VEC], fy[VEC], ox[VEC], oy[VEC], oz[VEC];
+    consume_tile<NP>(stage_mem + (size_t)s * FLOATS, tv, d1, m2, sx, sy, sz, fx, fy);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    const int bl = tile / tiles_per_pair, t = tile - bl * tiles_per_pair;
+    const int p = t * TILE + tv;
+    if (p >= HW) continue;
+    const PoseC& ps = c_pose[slot][bl];
+    const size_t b = (size_t)(b0 + bl);
+    const float* d2img = depth_2 + b * HW;
+    float* gd2img = g_d2 ? g_d2 + b * HW : nullptr;
+    const int y = p / W, x0 = p - y * W;
+    const float yf = (float)y;
+    float rn[3], ra[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      rn[k] = fmaf(ps.nM1[3 * k + 1], yf, ps.nM1[3 * k + 2]);
+      ra[k] = fmaf(ps.A[3 * k + 1], yf, ps.A[3 * k + 2]);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const int j = 2 * q;
+      const float xf = (float)(x0 + j);
+      const float2 nx = make_float2(-xf, -xf - 1.0f);
+      float2 gv0, gv1, gv2;
+      pair_backward(ps, cfg, d2img, gd2img, H, W, nx, -yf, make_float2(fx[j], fx[j + 1]), make_float2(fy[j], fy[j + 1]),
+                    make_float2(d1[j], d1[j + 1]), make_float2(m2[j], m2[j + 1]), make_float2(sx[j], sx[j + 1]),
+                    make_float2(sy[j], sy[j + 1]), make_float2(sz[j], sz[j + 1]), rn, ra, cf, cd, gv0, gv1, gv2);
+      ox[j] = gv0.x; ox[j + 1] = gv0.y; oy[j] = gv1.x; oy[j + 1] = gv1.y; oz[j] = gv2.x; oz[j + 1] = gv2.y;
+    }
+    float* gsp = g_sf + b * 3 * HW + p;
+    store_vec<VEC>(gsp, ox);
+    store_vec<VEC>(gsp + HW, oy);
+    store_vec<VEC>(gsp + 2 * (size_t)HW, oz);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs, int max_vec = 4) {
   bool al = true;
@@ -688,6 +1312,23 @@ static dim3 grid_bound(int B, int items_per_pair) {
   return dim3((unsigned)per_pair, (unsigned)B, 1);
 }
 
+// stage the derived poses of pairs [b0, b0 + nb) into a constant-memory slot (all on `st`, no host synchronisation)
+static int stage_poses(const float* poses, int b0, int nb, cudaStream_t st, int* slot_out) {
+  static std::atomic<unsigned> ctr{0};
+  static PoseC* stage = [] {
+    void* p = nullptr;
+    return cudaGetSymbolAddress(&p, g_pose_stage) == cudaSuccess ? static_cast<PoseC*>(p) : nullptr;
+  }();
+  DVD_ARG_CHECK(stage != nullptr, "cudaGetSymbolAddress(g_pose_stage) failed");
+  const int slot = (int)(ctr.fetch_add(1u) % (unsigned)kPoseSlots);
+  pose_prep_kernel<<<1, kPosePairs, 0, st>>>(poses + (size_t)b0 * DVD_POSE_STRIDE, nb, slot);
+  DVD_CUDA_LAUNCH_CHECK("pose_prep");
+  DVD_CUDA_CALL(cudaMemcpyToSymbolAsync(c_pose, stage + (size_t)slot * kPosePairs, (size_t)nb * sizeof(PoseC),
+                                        (size_t)slot * kPosePairs * sizeof(PoseC), cudaMemcpyDeviceToDevice, st));
+  *slot_out = slot;
+  return 0;
+}
+
 static int check_shape(int B, int H, int W) {
   DVD_ARG_CHECK(B >= 1 && H >= 2 && W >= 2, "bad shape B=%d H=%d W=%d (need B>=1, H,W>=2)", B, H, W);
   DVD_ARG_CHECK(B <= 65535, "B=%d exceeds gridDim.y", B);
@@ -703,7 +1344,11 @@ extern "C" int dvd_reproject_partials_size(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1) return 0;
   // upper bound over every VEC choice
   dim3 g = grid_bound(B, H * W);
-  return (int)(g.x * g.y * 4);
+  long quads = (long)g.x * g.y;
+  // staged forward: one quad per persistent CTA, per chunk of kPosePairs pairs
+  const long staged = (long)((B + kPosePairs - 1) / kPosePairs) * 4 * num_sms();
+  if (staged > quads) quads = staged;
+  return (int)(quads * 4);
 }
 
 extern "C" int dvd_unproject_fwd(const float* depth, const float* poses, float* P, int B, int H, int W, int which,
@@ -755,6 +1400,54 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
   const int ipp = H * W / vec;
   dim3 g;
   static const int minb = getenv("DVD_REPROJECT_MINB") ? atoi(getenv("DVD_REPROJECT_MINB")) : 3;
+  static const bool packed = !(getenv("DVD_REPROJECT_SCALAR") && atoi(getenv("DVD_REPROJECT_SCALAR")));
+  static const bool staged = !(getenv("DVD_REPROJECT_STAGED") && !atoi(getenv("DVD_REPROJECT_STAGED")));
+  if (vec == 4 && packed && staged) {
+    static const bool dry = getenv("DVD_REPROJECT_DRY") && atoi(getenv("DVD_REPROJECT_DRY"));
+    // variant = NP * 10 + CTAs per SM (DVD_REPROJECT_FWD_VARIANT); ring depth fixed per variant
+    static const int variant = getenv("DVD_REPROJECT_FWD_VARIANT") ? atoi(getenv("DVD_REPROJECT_FWD_VARIANT")) : 22;
+    struct Launch { const void* fn; int np, stages, ctas; };
+    auto pick = [&]() -> Launch {
+      if (dry) return {(const void*)reproject_loss_fwd_staged_kernel<2, 3, 2, true>, 2, 3, 2};
+      switch (variant) {
+        case 13: return {(const void*)reproject_loss_fwd_staged_kernel<1, 4, 3, false>, 1, 4, 3};
+        case 14: return {(const void*)reproject_loss_fwd_staged_kernel<1, 3, 4, false>, 1, 3, 4};
+        case 23: return {(const void*)reproject_loss_fwd_staged_kernel<2, 2, 3, false>, 2, 2, 3};
+        default: return {(const void*)reproject_loss_fwd_staged_kernel<2, 3, 2, false>, 2, 3, 2};
+      }
+    };
+    const Launch L = pick();
+    const int tile = kThreads * 2 * L.np, smem = L.stages * tile * 7 * 4;
+    DVD_CUDA_CALL(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int tiles_per_pair = (H * W + tile - 1) / tile;
+    unsigned nq = 0;
+    for (int b0 = 0; b0 < B; b0 += kPosePairs) {
+      int nb = B - b0 < kPosePairs ? B - b0 : kPosePairs;
+      int slot = 0;
+      if (int e = stage_poses(poses, b0, nb, st, &slot)) return e;
+      int gx = nb * tiles_per_pair;
+      if (gx > L.ctas * num_sms()) gx = L.ctas * num_sms();
+      float* part = partials + (size_t)nq * 4;
+      int b0v = b0, tpp = tiles_per_pair, Hh = H, Ww = W;
+      dvd_loss_cfg cfgv = *cfg;
+      void* args[] = {(void*)&depth_1, (void*)&depth_2, (void*)&flow_1_2, (void*)&mask_2, (void*)&sf, (void*)&cfgv, (void*)&part,
+                      (void*)&Hh, (void*)&Ww, (void*)&slot, (void*)&b0v, (void*)&nb, (void*)&tpp};
+      DVD_CUDA_CALL(cudaLaunchKernel(L.fn, dim3((unsigned)gx), dim3(kThreads + 32), args, (size_t)smem, st));
+      nq += (unsigned)gx;
+    }
+    g = dim3(nq, 1, 1);
+  } else if (vec == 4 && packed) {
+    g = grid_for(reproject_loss_fwd_f2_kernel<3>, B, ipp);
+    for (int b0 = 0; b0 < B; b0 += kPosePairs) {
+      const int nb = B - b0 < kPosePairs ? B - b0 : kPosePairs;
+      int slot = 0;
+      if (int e = stage_poses(poses, b0, nb, st, &slot)) return e;
+      dim3 gc(g.x, (unsigned)nb, 1);
+      if (minb >= 4) reproject_loss_fwd_f2_kernel<4><<<gc, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, *cfg, partials, H, W, slot, b0, (int)g.x);
+      else reproject_loss_fwd_f2_kernel<3><<<gc, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, *cfg, partials, H, W, slot, b0, (int)g.x);
+      DVD_CUDA_LAUNCH_CHECK("reproject_loss_fwd_f2");
+    }
+  } else {
   if (vec == 4 && minb >= 4) g = grid_for(reproject_loss_fwd_kernel<4, 4>, B, ipp);
   else if (vec == 4) g = grid_for(reproject_loss_fwd_kernel<4, 3>, B, ipp);
   else if (vec == 2) g = grid_for(reproject_loss_fwd_kernel<2, 4>, B, ipp);
@@ -763,6 +1456,7 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
   else if (vec == 4) reproject_loss_fwd_kernel<4, 3><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
   else if (vec == 2) reproject_loss_fwd_kernel<2, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
   else reproject_loss_fwd_kernel<1, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+  }
   DVD_CUDA_LAUNCH_CHECK("reproject_loss_fwd");
   reproject_finalize_kernel<<<1, 256, 0, st>>>(partials, (int)(g.x * g.y), *cfg, scalars);
   DVD_CUDA_LAUNCH_CHECK("reproject_finalize");
@@ -778,8 +1472,56 @@ extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2
   DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && mask_2 && sf && poses && scalars && g_sf, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_depth_2) DVD_CUDA_CALL(cudaMemsetAsync(g_depth_2, 0, (size_t)B * H * W * sizeof(float), st));
+  if (getenv("DVD_REPROJECT_BWD_NOSCATTER")) g_depth_2 = nullptr;   // profiling probe only: skip the scatter-add
   // measured on B200 (profiles/r1_reproject_vec_sweep.txt): the scatter-add backward is fastest with one pixel per
   // thread (1.97 TB/s vs 1.28 / 1.46 for 2 / 4): more warps in flight hide the red.global latency
+  static const bool packed = !(getenv("DVD_REPROJECT_SCALAR") && atoi(getenv("DVD_REPROJECT_SCALAR")));
+  static const int bwd_np = getenv("DVD_REPROJECT_BWD_NP") ? atoi(getenv("DVD_REPROJECT_BWD_NP")) : 1;
+  int vecp = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2, g_sf}, bwd_np >= 2 ? 4 : 2);   // DVD_REPROJECT_BWD_NP=2: 4 px / thread
+  static const bool staged = !(getenv("DVD_REPROJECT_STAGED") && !atoi(getenv("DVD_REPROJECT_STAGED")));
+  if (packed && staged && vecp >= 2 && (H * W) % 4 == 0) {
+    // variant = NP * 10 + CTAs per SM (DVD_REPROJECT_BWD_VARIANT)
+    static const int variant = getenv("DVD_REPROJECT_BWD_VARIANT") ? atoi(getenv("DVD_REPROJECT_BWD_VARIANT")) : 12;
+    struct Launch { const void* fn; int np, stages, ctas; };
+    auto pick = [&]() -> Launch {
+      if (vecp == 4 && variant == 21) return {(const void*)reproject_loss_bwd_staged_kernel<2, 3, 1>, 2, 3, 1};
+      if (variant == 13) return {(const void*)reproject_loss_bwd_staged_kernel<1, 4, 3>, 1, 4, 3};
+      if (variant == 14) return {(const void*)reproject_loss_bwd_staged_kernel<1, 3, 4>, 1, 3, 4};
+      return {(const void*)reproject_loss_bwd_staged_kernel<1, 4, 2>, 1, 4, 2};
+    };
+    const Launch L = pick();
+    const int tile = kThreads * 2 * L.np, smem = L.stages * tile * 7 * 4;
+    DVD_CUDA_CALL(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int tiles_per_pair = (H * W + tile - 1) / tile;
+    for (int b0 = 0; b0 < B; b0 += kPosePairs) {
+      int nb = B - b0 < kPosePairs ? B - b0 : kPosePairs;
+      int slot = 0;
+      if (int e = stage_poses(poses, b0, nb, st, &slot)) return e;
+      int gx = nb * tiles_per_pair;
+      if (gx > L.ctas * num_sms()) gx = L.ctas * num_sms();
+      int b0v = b0, tpp = tiles_per_pair, Hh = H, Ww = W;
+      dvd_loss_cfg cfgv = *cfg;
+      void* args[] = {(void*)&depth_1, (void*)&depth_2, (void*)&flow_1_2, (void*)&mask_2, (void*)&sf, (void*)&cfgv, (void*)&scalars,
+                      (void*)&gscale, (void*)&gscale_dev, (void*)&g_sf, (void*)&g_depth_2, (void*)&Hh, (void*)&Ww, (void*)&slot,
+                      (void*)&b0v, (void*)&nb, (void*)&tpp};
+      DVD_CUDA_CALL(cudaLaunchKernel(L.fn, dim3((unsigned)gx), dim3(kThreads + 32), args, (size_t)smem, st));
+    }
+    return 0;
+  }
+  if (packed && vecp >= 2) {
+    const int ipp = H * W / vecp;
+    dim3 g = vecp == 4 ? grid_for(reproject_loss_bwd_f2_kernel<2>, B, ipp) : grid_for(reproject_loss_bwd_f2_kernel<1>, B, ipp);
+    for (int b0 = 0; b0 < B; b0 += kPosePairs) {
+      const int nb = B - b0 < kPosePairs ? B - b0 : kPosePairs;
+      int slot = 0;
+      if (int e = stage_poses(poses, b0, nb, st, &slot)) return e;
+      dim3 gc(g.x, (unsigned)nb, 1);
+      if (vecp == 4) reproject_loss_bwd_f2_kernel<2><<<gc, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W, slot, b0);
+      else reproject_loss_bwd_f2_kernel<1><<<gc, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W, slot, b0);
+      DVD_CUDA_LAUNCH_CHECK("reproject_loss_bwd_f2");
+    }
+    return 0;
+  }
   int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2, g_sf}, 1);
   const int ipp = H * W / vec;
   dim3 g = vec == 4 ? grid_for(reproject_loss_bwd_kernel<4>, B, ipp)
