@@ -220,15 +220,16 @@ def roofline_reproject(pairs, hbm_peak, peak_kind):
         t = sum(ts) / len(ts)
         out.append({'kernel': name, 'bytes_per_px': bpp, 'us': t * 1e6, 'achieved': px * bpp / t / 1e9,
                     'frac': px * bpp / t / 1e9 / hbm_peak})
-    # DRAM traffic per pixel from the committed ncu captures (profiles/r1_ncu_reproject_{fwd,bwd}_v3.json,
-    # dram__bytes_read.sum + dram__bytes_write.sum of one 64-pair launch / 5 505 024 px): no re-reads.
-    ncu_bpp = {'reproject_loss_fwd_kernel': 32.8, 'reproject_loss_bwd_kernel': 47.4}
+    # DRAM traffic per pixel from the committed ncu pass (profiles/r1_ncu_reproject_variants.txt: dram__bytes_read.sum +
+    # dram__bytes_write.sum of one 64-pair launch / 5 505 024 px): no re-reads.
+    ncu_bpp = {'reproject_loss_fwd_kernel': 32.7, 'reproject_loss_bwd_kernel': 46.3}
     tot_t = sum(k['us'] for k in out) * 1e-6
     dom = max(out[1:3], key=lambda k: k['us'])
     return {'bound': 'hbm', 'kernel': dom['kernel'], 'achieved': dom['achieved'], 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': dom['frac'], 'traffic': ncu_bpp[dom['kernel']] * px, 'traffic_unit': 'bytes/launch (ncu DRAM read+write)',
             'algorithmic_bytes': dom['bytes_per_px'] * px, 'peak_kind': peak_kind,
-            'note': 'fp32 chain is co-limited by FP32 issue rate: ~150 FP ops + ~70 other instructions per pixel (DESIGN.md 4.1)',
+            'note': 'whole C-ABI call between the events (memset of g_depth_2 + pose staging + kernel); kernel alone under ncu: bwd 105 us, fwd 52 us '
+                    '(profiles/r1_ncu_reproject_variants.txt); the scatter-add of g_depth_2 (4 reductions / px) is ~1/3 of the backward (DESIGN.md 4.1)',
             'how': 'CUDA events in bench.py, %d pairs per launch (%.0f MB algorithmic traffic), 256 MB L2 flush between launches'
                    % (pairs, px * dom['bytes_per_px'] / 1e6),
             'chain_112B_per_px': {'achieved': px * 112 / tot_t / 1e9, 'frac': px * 112 / tot_t / 1e9 / hbm_peak},

@@ -728,8 +728,42 @@ struct PairOut {
   bool zok[2];
 };
 
-template <bool kWorld>
-__device__ __forceinline__ void pair_forward(const PoseC& ps, const float* __restrict__ d2img, int H, int W, float2 nx,
+// Where the four bilinear taps of a pixel come from / where their gradients go.
+struct GlobalTaps {
+  const float* img;   // depth_2 of this pair
+  __device__ __forceinline__ void ld4(int i00, int sx1, int sy1, float (&d)[4]) const {
+    const float* p = img + i00;   // one 64-bit address per pixel, the other taps at small element offsets from it
+    d[0] = __ldg(p); d[1] = __ldg(p + sx1); d[2] = __ldg(p + sy1); d[3] = __ldg(p + sy1 + sx1);
+  }
+};
+__device__ __forceinline__ void red_global_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+// scatter-add of the four tap gradients of one pixel; the packed kernels require W % 4 == 0, so whenever the nw tap sits
+// on an even column the (nw, ne) and (sw, se) taps are two 8-byte aligned pairs: one vector reduction each
+__device__ __forceinline__ void scatter4_global(float* q, int i00, int sx1, int sy1, const float (&g)[4]) {
+  if (((i00 & 1) == 0) && sx1 == 1) {
+    if (g[0] != 0.f || g[1] != 0.f) red_global_v2(q, g[0], g[1]);
+    if (g[2] != 0.f || g[3] != 0.f) {
+      if (sy1 != 0) red_global_v2(q + sy1, g[2], g[3]);
+      else red_global_v2(q, g[2], g[3]);     // clamped bottom row: both weights are exactly 0 here, kept for form
+    }
+  } else {
+    if (g[0] != 0.f) atomicAdd(q, g[0]);
+    if (g[1] != 0.f) atomicAdd(q + sx1, g[1]);
+    if (g[2] != 0.f) atomicAdd(q + sy1, g[2]);
+    if (g[3] != 0.f) atomicAdd(q + sy1 + sx1, g[3]);
+  }
+}
+struct GlobalScatter {
+  float* gimg;        // g_depth_2 of this pair (nullptr: no scatter)
+  __device__ __forceinline__ bool on() const { return gimg != nullptr; }
+  __device__ __forceinline__ void add4(int i00, int sx1, int sy1, const float (&g)[4]) const {
+    scatter4_global(gimg + i00, i00, sx1, sy1, g);
+  }
+};
+template <bool kWorld, class Taps>
+__device__ __forceinline__ void pair_forward(const PoseC& ps, const Taps& taps, int H, int W, float2 nx,
                                              float nyf, float2 fx, float2 fy, float2 d1, float2 sx, float2 sy, float2 sz,
                                              const float (&rn)[3], const float (&ra)[3], PairOut& o) {
   const float hw = (float)(W - 1), hh = (float)(H - 1);
@@ -750,13 +784,11 @@ __device__ __forceinline__ void pair_forward(const PoseC& ps, const float* __res
   }
   float2 dk[4];
   {
-    // one 64-bit address per pixel, the other taps at small element offsets from it
-    const float* pa = d2img + o.i00[0];
-    const float* pb = d2img + o.i00[1];
-    dk[0] = make_float2(__ldg(pa), __ldg(pb));
-    dk[1] = make_float2(__ldg(pa + o.sx1[0]), __ldg(pb + o.sx1[1]));
-    dk[2] = make_float2(__ldg(pa + o.sy1[0]), __ldg(pb + o.sy1[1]));
-    dk[3] = make_float2(__ldg(pa + o.sy1[0] + o.sx1[0]), __ldg(pb + o.sy1[1] + o.sx1[1]));
+    float da[4], db[4];
+    taps.ld4(o.i00[0], o.sx1[0], o.sy1[0], da);
+    taps.ld4(o.i00[1], o.sx1[1], o.sy1[1], db);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dk[k] = make_float2(da[k], db[k]);
   }
   // ---- arithmetic that does not depend on the gathered taps first: it runs while the gather is in flight ----
   // p12 = d1 (A c) + cv + R2^T sf ; c = (x, y, 1): A c = A[:,0] x + (A[:,1] y + A[:,2]) = -A[:,0] nx + ra
@@ -812,98 +844,14 @@ __device__ __forceinline__ float mask1(const dvd_loss_cfg& c, float m2, float d1
   return (!c.midas || (d1 < 100.0f && wz < 100.0f)) ? m2 : 0.0f;
 }
 
-// fused forward, 4 pixels (two pairs) per thread
-template <int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) reproject_loss_fwd_f2_kernel(
-    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
-    const float* __restrict__ mask_2, const float* __restrict__ sf, dvd_loss_cfg cfg, float* __restrict__ partials,
-    int H, int W, int slot, int b0, int slots_per_pair) {
-  __shared__ float red[kThreads / 32][4];
-  const PoseC& ps = c_pose[slot][blockIdx.y];
-  const int b = b0 + blockIdx.y;
-  const int HW = H * W, items = HW / 4, Wv = W / 4;
-  const float* d2img = depth_2 + (size_t)b * HW;
-  float2 a_flow = F2(0.f), a_disp = F2(0.f), a_sf = F2(0.f), a_m = F2(0.f);
-  const int stride = gridDim.x * blockDim.x, sdy = stride / Wv, sdx = stride - sdy * Wv;
-  int it = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = it / Wv, xv = it - y * Wv;
-  for (; it < items; it += stride, y += sdy, xv += sdx) {
-    if (xv >= Wv) { xv -= Wv; ++y; }
-    const int x0 = xv * 4;
-    const size_t pix = (size_t)y * W + x0;
-    const float4 d1 = ldg_stream4(depth_1 + (size_t)b * HW + pix);
-    const float4 m2 = ldg_stream4(mask_2 + (size_t)b * HW + pix);
-    const float* sfp = sf + (size_t)b * 3 * HW + pix;
-    const float4 sx = ldg_stream4(sfp), sy = ldg_stream4(sfp + HW), sz = ldg_stream4(sfp + 2 * (size_t)HW);
-    const float* fp = flow + ((size_t)b * HW + pix) * 2;
-    const float4 fa = ldg_stream4(fp), fb = ldg_stream4(fp + 4);
-    const float yf = (float)y;
-    float rn[3], ra[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      rn[k] = fmaf(ps.nM1[3 * k + 1], yf, ps.nM1[3 * k + 2]);
-      ra[k] = fmaf(ps.A[3 * k + 1], yf, ps.A[3 * k + 2]);
-    }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const float xf = (float)(x0 + 2 * p);
-      const float2 nx = make_float2(-xf, -xf - 1.0f);
-      const float2 fx = p == 0 ? make_float2(fa.x, fa.z) : make_float2(fb.x, fb.z);
-      const float2 fy = p == 0 ? make_float2(fa.y, fa.w) : make_float2(fb.y, fb.w);
-      const float2 dd = p == 0 ? make_float2(d1.x, d1.y) : make_float2(d1.z, d1.w);
-      const float2 mm = p == 0 ? make_float2(m2.x, m2.y) : make_float2(m2.z, m2.w);
-      const float2 px = p == 0 ? make_float2(sx.x, sx.y) : make_float2(sx.z, sx.w);
-      const float2 py = p == 0 ? make_float2(sy.x, sy.y) : make_float2(sy.z, sy.w);
-      const float2 pz = p == 0 ? make_float2(sz.x, sz.y) : make_float2(sz.z, sz.w);
-      PairOut o;
-      pair_forward<true>(ps, d2img, H, W, nx, -yf, fx, fy, dd, px, py, pz, rn, ra, o);
-      const float2 m = make_float2(mask1(cfg, mm.x, dd.x, o.wpc[2].x), mask1(cfg, mm.y, dd.y, o.wpc[2].y));
-      float2 fl, dl, sl;
-      if (cfg.warm) fl = fma2(o.ex, o.ex, mul2(o.ey, o.ey));
-      else fl = make_float2(fabsf(o.ex.x) + fabsf(o.ey.x), fabsf(o.ex.y) + fabsf(o.ey.y));
-      dl = make_float2(disp_term(cfg, o.p12[2].x, o.wpc[2].x), disp_term(cfg, o.p12[2].y, o.wpc[2].y));
-      sl = make_float2(fabsf(o.e[0].x) + fabsf(o.e[1].x) + fabsf(o.e[2].x), fabsf(o.e[0].y) + fabsf(o.e[1].y) + fabsf(o.e[2].y));
-      a_flow = fma2(m, fl, a_flow);
-      a_disp = fma2(m, dl, a_disp);
-      a_sf = fma2(m, sl, a_sf);
-      a_m = add2(a_m, m);
-    }
-  }
-  float s_flow = warp_sum(a_flow.x + a_flow.y), s_disp = warp_sum(a_disp.x + a_disp.y);
-  float s_sf = warp_sum(a_sf.x + a_sf.y), s_m = warp_sum(a_m.x + a_m.y);
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { red[wid][0] = s_flow; red[wid][1] = s_disp; red[wid][2] = s_sf; red[wid][3] = s_m; }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    float a = 0.f;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) a += red[w][threadIdx.x];
-    partials[((size_t)b * slots_per_pair + blockIdx.x) * 4 + threadIdx.x] = a;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Staged variant: the five streamed inputs (28 of the 32 bytes per pixel) travel global -> shared memory as 1-D bulk
-// async copies issued by a producer warp into a ring of kRStages tiles, completion on mbarriers; the 256 consumer threads
-// only see shared-memory latency for them, and the bytes in flight per SM (2 CTAs x kRStages x 28 KB) no longer depend
-// on occupancy or on how the compiler schedules the loads. Only the bilinear gather of depth_2 is a global load.
-// bring [p, p + bytes) into L2 (hint only; bytes multiple of 16)
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-// The gathered image depth_2 of the whole chunk (nb x HW floats, 22 MB at 64 pairs of 384x224) fits in L2 many times
-// over: every CTA prefetches an equal slice up front so that the data-dependent bilinear taps find their sectors in L2
-// instead of paying a second DRAM round trip behind the streamed loads.
-__device__ __forceinline__ void prefetch_gather_image(const float* d2chunk, size_t floats) {
-  const size_t bytes = floats * 4, per = ((bytes + gridDim.x - 1) / gridDim.x + 15) & ~(size_t)15;
-  size_t lo = (size_t)blockIdx.x * per, hi = lo + per < bytes ? lo + per : bytes;
-  const char* base = reinterpret_cast<const char*>(d2chunk);
-  for (size_t o = lo + (size_t)(threadIdx.x & 31) * 4096; o < hi; o += 32 * 4096) {
-    const size_t n = hi - o < 4096 ? hi - o : 4096;
-    l2_prefetch_bulk(base + o, (uint32_t)(n & ~(size_t)15));
-  }
-}
-
+// async copies issued by a producer warp into a ring of STAGES tiles, completion on mbarriers; the 256 consumer threads
+// only see shared-memory latency for them, and the bytes in flight per SM (CTAs x STAGES x 14 KB) no longer depend on
+// occupancy or on how the compiler schedules the loads. Only the bilinear gather of depth_2 is a global load.
+// Measured dead ends (profiles/r1_ncu_reproject_variants.txt): also staging the depth_2 rows around the tile in shared
+// memory (taps as LDS) is not faster, and accumulating g_depth_2 in a shared-memory window is not either - fp32
+// red.shared compiles to an ATOMS.CAST.SPIN compare-and-swap loop on sm_100.
 template <int NP> struct StagedCfg {
   static constexpr int VEC = 2 * NP;                 // pixels per consumer thread and tile
   static constexpr int TILE = kThreads * VEC;        // pixels per stage
@@ -913,9 +861,9 @@ template <int NP> struct StagedCfg {
 // stream one tile (pixels [p0, p0 + n) of pair b) into a stage
 template <int TILE>
 __device__ __forceinline__ void produce_tile(float* dst, uint64_t* bar, const float* depth_1, const float* mask_2,
-                                             const float* sf, const float* flow, size_t b, int HW, int p0) {
+                                             const float* sf, const float* flow, size_t b, int HW, int p0, int pend) {
   using namespace tc;
-  const uint32_t n4 = (uint32_t)min(TILE, HW - p0) * 4u;
+  const uint32_t n4 = (uint32_t)min(TILE, pend - p0) * 4u;
   mbar_arrive_expect_tx(bar, n4 * 7u);
   bulk_g2s(dst, depth_1 + b * HW + p0, n4, bar);
   bulk_g2s(dst + TILE, mask_2 + b * HW + p0, n4, bar);
@@ -978,7 +926,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) reproject_loss_fwd_staged
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         const int bl = tile / tiles_per_pair, t = tile - bl * tiles_per_pair;
-        produce_tile<TILE>(stage_mem + (size_t)s * FLOATS, &full[s], depth_1, mask_2, sf, flow, (size_t)(b0 + bl), HW, t * TILE);
+        produce_tile<TILE>(stage_mem + (size_t)s * FLOATS, &full[s], depth_1, mask_2, sf, flow, (size_t)(b0 + bl), HW, t * TILE, HW);
       }
     }
     return;
@@ -1021,7 +969,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) reproject_loss_fwd_staged
       const float2 nx = make_float2(-xf, -xf - 1.0f);
       const float2 dd = make_float2(d1[j], d1[j + 1]);
       PairOut o;
-      pair_forward<true>(ps, d2img, H, W, nx, -yf, make_float2(fx[j], fx[j + 1]), make_float2(fy[j], fy[j + 1]), dd,
+      pair_forward<true>(ps, GlobalTaps{d2img}, H, W, nx, -yf, make_float2(fx[j], fx[j + 1]), make_float2(fy[j], fy[j + 1]), dd,
                          make_float2(sx[j], sx[j + 1]), make_float2(sy[j], sy[j + 1]), make_float2(sz[j], sz[j + 1]), rn, ra, o);
       const float2 m = make_float2(mask1(cfg, m2[j], dd.x, o.wpc[2].x), mask1(cfg, m2[j + 1], dd.y, o.wpc[2].y));
       float2 fl, dl, sl;
@@ -1055,8 +1003,9 @@ __device__ __forceinline__ float2 sgn_scale2(float2 v, float2 c) {
 }
 
 // backward of one pixel pair: returns g_(P1 + sf) and scatters g_depth_2
-__device__ __forceinline__ void pair_backward(const PoseC& ps, const dvd_loss_cfg& cfg, const float* __restrict__ d2img,
-                                              float* __restrict__ gd2img, int H, int W, float2 nx, float nyf, float2 fx,
+template <class Taps, class Scat>
+__device__ __forceinline__ void pair_backward(const PoseC& ps, const dvd_loss_cfg& cfg, const Taps& d2img,
+                                              const Scat& scat, int H, int W, float2 nx, float nyf, float2 fx,
                                               float2 fy, float2 dd, float2 mm, float2 psx, float2 psy, float2 psz,
                                               const float (&rn)[3], const float (&ra)[3], float cf, float cd, float2& gv0,
                                               float2& gv1, float2& gv2) {
@@ -1124,80 +1073,15 @@ __device__ __forceinline__ void pair_backward(const PoseC& ps, const dvd_loss_cf
       mv2(ps.R2, gp0, gp1, gp2, gv0, gv1, gv2);
       gv0 = sub2(gv0, ge0); gv1 = sub2(gv1, ge1); gv2 = sub2(gv2, ge2);
       // scatter to depth_2: g_d2_k = w_k (hu u_k + hv v_k + h1), (u_k, v_k) = (x0f, y0f) (+1)
-      if (gd2img) {
+      if (scat.on()) {
         const float2 base = fma2(hu, o.x0f, fma2(hv, o.y0f, h1));
         const float2 bx = add2(base, hu);
         const float2 g0 = mul2(o.w[0], base), g1 = mul2(o.w[1], bx);
         const float2 g2 = mul2(o.w[2], add2(base, hv)), g3 = mul2(o.w[3], add2(bx, hv));
-        float* qa = gd2img + o.i00[0];
-        float* qb = gd2img + o.i00[1];
-        if (g0.x != 0.f) atomicAdd(qa, g0.x);
-        if (g1.x != 0.f) atomicAdd(qa + o.sx1[0], g1.x);
-        if (g2.x != 0.f) atomicAdd(qa + o.sy1[0], g2.x);
-        if (g3.x != 0.f) atomicAdd(qa + o.sy1[0] + o.sx1[0], g3.x);
-        if (g0.y != 0.f) atomicAdd(qb, g0.y);
-        if (g1.y != 0.f) atomicAdd(qb + o.sx1[1], g1.y);
-        if (g2.y != 0.f) atomicAdd(qb + o.sy1[1], g2.y);
-        if (g3.y != 0.f) atomicAdd(qb + o.sy1[1] + o.sx1[1], g3.y);
+        const float ga[4] = {g0.x, g1.x, g2.x, g3.x}, gb[4] = {g0.y, g1.y, g2.y, g3.y};
+        scat.add4(o.i00[0], o.sx1[0], o.sy1[0], ga);
+        scat.add4(o.i00[1], o.sx1[1], o.sy1[1], gb);
       }
-}
-
-// fused backward, NP pixel pairs per thread: g_sf (== g_global_p1) and the scatter-add of g_depth_2
-template <int NP>
-__global__ void __launch_bounds__(kThreads) reproject_loss_bwd_f2_kernel(
-    const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
-    const float* __restrict__ mask_2, const float* __restrict__ sf, dvd_loss_cfg cfg, const float* __restrict__ scalars,
-    float gscale, const float* __restrict__ gscale_dev, float* __restrict__ g_sf, float* __restrict__ g_d2, int H, int W,
-    int slot, int b0) {
-  constexpr int VEC = 2 * NP;
-  const PoseC& ps = c_pose[slot][blockIdx.y];
-  const int b = b0 + blockIdx.y;
-  const float gs = gscale * (gscale_dev ? __ldg(gscale_dev) : 1.0f);
-  const float cf = __ldg(scalars + DVD_S_CF) * gs;
-  const float cd = __ldg(scalars + DVD_S_CD) * gs;
-  const int HW = H * W, items = HW / VEC, Wv = W / VEC;
-  const float* d2img = depth_2 + (size_t)b * HW;
-  float* gd2img = g_d2 ? g_d2 + (size_t)b * HW : nullptr;
-  const int stride = gridDim.x * blockDim.x, sdy = stride / Wv, sdx = stride - sdy * Wv;
-  int it = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = it / Wv, xv = it - y * Wv;
-  for (; it < items; it += stride, y += sdy, xv += sdx) {
-    if (xv >= Wv) { xv -= Wv; ++y; }
-    const int x0 = xv * VEC;
-    const size_t pix = (size_t)y * W + x0;
-    float d1[VEC], m2[VEC], sx[VEC], sy[VEC], sz[VEC], fx[VEC], fy[VEC];
-    float ox[VEC], oy[VEC], oz[VEC];
-    load_vec<VEC>(depth_1 + (size_t)b * HW + pix, d1);
-    load_vec<VEC>(mask_2 + (size_t)b * HW + pix, m2);
-    const float* sfp = sf + (size_t)b * 3 * HW + pix;
-    load_vec<VEC>(sfp, sx);
-    load_vec<VEC>(sfp + HW, sy);
-    load_vec<VEC>(sfp + 2 * (size_t)HW, sz);
-    load_flow<VEC>(flow + ((size_t)b * HW + pix) * 2, fx, fy);
-    const float yf = (float)y;
-    float rn[3], ra[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      rn[k] = fmaf(ps.nM1[3 * k + 1], yf, ps.nM1[3 * k + 2]);
-      ra[k] = fmaf(ps.A[3 * k + 1], yf, ps.A[3 * k + 2]);
-    }
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      const int j = 2 * p;
-      const float xf = (float)(x0 + j);
-      const float2 nx = make_float2(-xf, -xf - 1.0f);
-      const float2 dd = make_float2(d1[j], d1[j + 1]);
-      const float2 psx = make_float2(sx[j], sx[j + 1]), psy = make_float2(sy[j], sy[j + 1]), psz = make_float2(sz[j], sz[j + 1]);
-      float2 gv0, gv1, gv2;
-      pair_backward(ps, cfg, d2img, gd2img, H, W, nx, -yf, make_float2(fx[j], fx[j + 1]), make_float2(fy[j], fy[j + 1]), dd,
-                    make_float2(m2[j], m2[j + 1]), psx, psy, psz, rn, ra, cf, cd, gv0, gv1, gv2);
-      ox[j] = gv0.x; ox[j + 1] = gv0.y; oy[j] = gv1.x; oy[j + 1] = gv1.y; oz[j] = gv2.x; oz[j + 1] = gv2.y;
-    }
-    float* gsp = g_sf + (size_t)b * 3 * HW + pix;
-    store_vec<VEC>(gsp, ox);
-    store_vec<VEC>(gsp + HW, oy);
-    store_vec<VEC>(gsp + 2 * (size_t)HW, oz);
-  }
 }
 
 // staged backward (same producer / consumer ring as the staged forward), NP pixel pairs per consumer thread
@@ -1225,7 +1109,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) reproject_loss_bwd_staged
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         const int bl = tile / tiles_per_pair, t = tile - bl * tiles_per_pair;
-        produce_tile<TILE>(stage_mem + (size_t)s * FLOATS, &full[s], depth_1, mask_2, sf, flow, (size_t)(b0 + bl), HW, t * TILE);
+        produce_tile<TILE>(stage_mem + (size_t)s * FLOATS, &full[s], depth_1, mask_2, sf, flow, (size_t)(b0 + bl), HW, t * TILE, HW);
       }
     }
     return;
@@ -1263,7 +1147,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) reproject_loss_bwd_staged
       const float xf = (float)(x0 + j);
       const float2 nx = make_float2(-xf, -xf - 1.0f);
       float2 gv0, gv1, gv2;
-      pair_backward(ps, cfg, d2img, gd2img, H, W, nx, -yf, make_float2(fx[j], fx[j + 1]), make_float2(fy[j], fy[j + 1]),
+      pair_backward(ps, cfg, GlobalTaps{d2img}, GlobalScatter{gd2img}, H, W, nx, -yf, make_float2(fx[j], fx[j + 1]), make_float2(fy[j], fy[j + 1]),
                     make_float2(d1[j], d1[j + 1]), make_float2(m2[j], m2[j + 1]), make_float2(sx[j], sx[j + 1]),
                     make_float2(sy[j], sy[j + 1]), make_float2(sz[j], sz[j + 1]), rn, ra, cf, cd, gv0, gv1, gv2);
       ox[j] = gv0.x; ox[j + 1] = gv0.y; oy[j] = gv1.x; oy[j + 1] = gv1.y; oz[j] = gv2.x; oz[j + 1] = gv2.y;
@@ -1346,7 +1230,7 @@ extern "C" int dvd_reproject_partials_size(int B, int H, int W) {
   dim3 g = grid_bound(B, H * W);
   long quads = (long)g.x * g.y;
   // staged forward: one quad per persistent CTA, per chunk of kPosePairs pairs
-  const long staged = (long)((B + kPosePairs - 1) / kPosePairs) * 4 * num_sms();
+  const long staged = (long)((B + kPosePairs - 1) / kPosePairs) * 3 * num_sms();
   if (staged > quads) quads = staged;
   return (int)(quads * 4);
 }
@@ -1399,26 +1283,17 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
   int vec = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2});
   const int ipp = H * W / vec;
   dim3 g;
-  static const int minb = getenv("DVD_REPROJECT_MINB") ? atoi(getenv("DVD_REPROJECT_MINB")) : 3;
+  // DVD_REPROJECT_SCALAR=1 forces the generic scalar kernels (any shape); DVD_REPROJECT_DRY=1 is a memory-system probe
   static const bool packed = !(getenv("DVD_REPROJECT_SCALAR") && atoi(getenv("DVD_REPROJECT_SCALAR")));
-  static const bool staged = !(getenv("DVD_REPROJECT_STAGED") && !atoi(getenv("DVD_REPROJECT_STAGED")));
-  if (vec == 4 && packed && staged) {
-    static const bool dry = getenv("DVD_REPROJECT_DRY") && atoi(getenv("DVD_REPROJECT_DRY"));
-    // variant = NP * 10 + CTAs per SM (DVD_REPROJECT_FWD_VARIANT); ring depth fixed per variant
-    static const int variant = getenv("DVD_REPROJECT_FWD_VARIANT") ? atoi(getenv("DVD_REPROJECT_FWD_VARIANT")) : 22;
-    struct Launch { const void* fn; int np, stages, ctas; };
-    auto pick = [&]() -> Launch {
-      if (dry) return {(const void*)reproject_loss_fwd_staged_kernel<2, 3, 2, true>, 2, 3, 2};
-      switch (variant) {
-        case 13: return {(const void*)reproject_loss_fwd_staged_kernel<1, 4, 3, false>, 1, 4, 3};
-        case 14: return {(const void*)reproject_loss_fwd_staged_kernel<1, 3, 4, false>, 1, 3, 4};
-        case 23: return {(const void*)reproject_loss_fwd_staged_kernel<2, 2, 3, false>, 2, 2, 3};
-        default: return {(const void*)reproject_loss_fwd_staged_kernel<2, 3, 2, false>, 2, 3, 2};
-      }
-    };
-    const Launch L = pick();
-    const int tile = kThreads * 2 * L.np, smem = L.stages * tile * 7 * 4;
-    DVD_CUDA_CALL(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static const bool dry = getenv("DVD_REPROJECT_DRY") && atoi(getenv("DVD_REPROJECT_DRY"));
+  if (vec == 4 && packed) {
+    // packed-FP32 kernel, bulk-async staged inputs: 1 pixel pair per consumer thread, 4-deep ring, 3 CTAs per SM
+    // (fastest of the measured variants, profiles/r1_ncu_reproject_variants.txt)
+    const void* fn = dry ? (const void*)reproject_loss_fwd_staged_kernel<1, 4, 3, true>
+                         : (const void*)reproject_loss_fwd_staged_kernel<1, 4, 3, false>;
+    constexpr int np = 1, stages = 4, ctas = 3;
+    const int tile = kThreads * 2 * np, smem = stages * tile * 7 * 4;
+    DVD_CUDA_CALL(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int tiles_per_pair = (H * W + tile - 1) / tile;
     unsigned nq = 0;
     for (int b0 = 0; b0 < B; b0 += kPosePairs) {
@@ -1426,36 +1301,23 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
       int slot = 0;
       if (int e = stage_poses(poses, b0, nb, st, &slot)) return e;
       int gx = nb * tiles_per_pair;
-      if (gx > L.ctas * num_sms()) gx = L.ctas * num_sms();
+      if (gx > ctas * num_sms()) gx = ctas * num_sms();
       float* part = partials + (size_t)nq * 4;
       int b0v = b0, tpp = tiles_per_pair, Hh = H, Ww = W;
       dvd_loss_cfg cfgv = *cfg;
       void* args[] = {(void*)&depth_1, (void*)&depth_2, (void*)&flow_1_2, (void*)&mask_2, (void*)&sf, (void*)&cfgv, (void*)&part,
                       (void*)&Hh, (void*)&Ww, (void*)&slot, (void*)&b0v, (void*)&nb, (void*)&tpp};
-      DVD_CUDA_CALL(cudaLaunchKernel(L.fn, dim3((unsigned)gx), dim3(kThreads + 32), args, (size_t)smem, st));
+      DVD_CUDA_CALL(cudaLaunchKernel(fn, dim3((unsigned)gx), dim3(kThreads + 32), args, (size_t)smem, st));
       nq += (unsigned)gx;
     }
     g = dim3(nq, 1, 1);
-  } else if (vec == 4 && packed) {
-    g = grid_for(reproject_loss_fwd_f2_kernel<3>, B, ipp);
-    for (int b0 = 0; b0 < B; b0 += kPosePairs) {
-      const int nb = B - b0 < kPosePairs ? B - b0 : kPosePairs;
-      int slot = 0;
-      if (int e = stage_poses(poses, b0, nb, st, &slot)) return e;
-      dim3 gc(g.x, (unsigned)nb, 1);
-      if (minb >= 4) reproject_loss_fwd_f2_kernel<4><<<gc, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, *cfg, partials, H, W, slot, b0, (int)g.x);
-      else reproject_loss_fwd_f2_kernel<3><<<gc, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, *cfg, partials, H, W, slot, b0, (int)g.x);
-      DVD_CUDA_LAUNCH_CHECK("reproject_loss_fwd_f2");
-    }
   } else {
-  if (vec == 4 && minb >= 4) g = grid_for(reproject_loss_fwd_kernel<4, 4>, B, ipp);
-  else if (vec == 4) g = grid_for(reproject_loss_fwd_kernel<4, 3>, B, ipp);
-  else if (vec == 2) g = grid_for(reproject_loss_fwd_kernel<2, 4>, B, ipp);
-  else g = grid_for(reproject_loss_fwd_kernel<1, 4>, B, ipp);
-  if (vec == 4 && minb >= 4) reproject_loss_fwd_kernel<4, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
-  else if (vec == 4) reproject_loss_fwd_kernel<4, 3><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
-  else if (vec == 2) reproject_loss_fwd_kernel<2, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
-  else reproject_loss_fwd_kernel<1, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+    if (vec == 4) g = grid_for(reproject_loss_fwd_kernel<4, 3>, B, ipp);
+    else if (vec == 2) g = grid_for(reproject_loss_fwd_kernel<2, 4>, B, ipp);
+    else g = grid_for(reproject_loss_fwd_kernel<1, 4>, B, ipp);
+    if (vec == 4) reproject_loss_fwd_kernel<4, 3><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+    else if (vec == 2) reproject_loss_fwd_kernel<2, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+    else reproject_loss_fwd_kernel<1, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
   }
   DVD_CUDA_LAUNCH_CHECK("reproject_loss_fwd");
   reproject_finalize_kernel<<<1, 256, 0, st>>>(partials, (int)(g.x * g.y), *cfg, scalars);
@@ -1476,49 +1338,26 @@ extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2
   // measured on B200 (profiles/r1_reproject_vec_sweep.txt): the scatter-add backward is fastest with one pixel per
   // thread (1.97 TB/s vs 1.28 / 1.46 for 2 / 4): more warps in flight hide the red.global latency
   static const bool packed = !(getenv("DVD_REPROJECT_SCALAR") && atoi(getenv("DVD_REPROJECT_SCALAR")));
-  static const int bwd_np = getenv("DVD_REPROJECT_BWD_NP") ? atoi(getenv("DVD_REPROJECT_BWD_NP")) : 1;
-  int vecp = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2, g_sf}, bwd_np >= 2 ? 4 : 2);   // DVD_REPROJECT_BWD_NP=2: 4 px / thread
-  static const bool staged = !(getenv("DVD_REPROJECT_STAGED") && !atoi(getenv("DVD_REPROJECT_STAGED")));
-  if (packed && staged && vecp >= 2 && (H * W) % 4 == 0) {
-    // variant = NP * 10 + CTAs per SM (DVD_REPROJECT_BWD_VARIANT)
-    static const int variant = getenv("DVD_REPROJECT_BWD_VARIANT") ? atoi(getenv("DVD_REPROJECT_BWD_VARIANT")) : 12;
-    struct Launch { const void* fn; int np, stages, ctas; };
-    auto pick = [&]() -> Launch {
-      if (vecp == 4 && variant == 21) return {(const void*)reproject_loss_bwd_staged_kernel<2, 3, 1>, 2, 3, 1};
-      if (variant == 13) return {(const void*)reproject_loss_bwd_staged_kernel<1, 4, 3>, 1, 4, 3};
-      if (variant == 14) return {(const void*)reproject_loss_bwd_staged_kernel<1, 3, 4>, 1, 3, 4};
-      return {(const void*)reproject_loss_bwd_staged_kernel<1, 4, 2>, 1, 4, 2};
-    };
-    const Launch L = pick();
-    const int tile = kThreads * 2 * L.np, smem = L.stages * tile * 7 * 4;
-    DVD_CUDA_CALL(cudaFuncSetAttribute(L.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int vecp = pick_vec(B, H, W, {depth_1, mask_2, sf, flow_1_2, g_sf}, 4);
+  if (packed && vecp == 4) {
+    // packed-FP32 kernel, bulk-async staged inputs: 1 pixel pair per consumer thread, 4-deep ring, 2 CTAs per SM
+    const void* fn = (const void*)reproject_loss_bwd_staged_kernel<1, 4, 2>;
+    constexpr int np = 1, stages = 4, ctas = 2;
+    const int tile = kThreads * 2 * np, smem = stages * tile * 7 * 4;
+    DVD_CUDA_CALL(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int tiles_per_pair = (H * W + tile - 1) / tile;
     for (int b0 = 0; b0 < B; b0 += kPosePairs) {
       int nb = B - b0 < kPosePairs ? B - b0 : kPosePairs;
       int slot = 0;
       if (int e = stage_poses(poses, b0, nb, st, &slot)) return e;
       int gx = nb * tiles_per_pair;
-      if (gx > L.ctas * num_sms()) gx = L.ctas * num_sms();
+      if (gx > ctas * num_sms()) gx = ctas * num_sms();
       int b0v = b0, tpp = tiles_per_pair, Hh = H, Ww = W;
       dvd_loss_cfg cfgv = *cfg;
       void* args[] = {(void*)&depth_1, (void*)&depth_2, (void*)&flow_1_2, (void*)&mask_2, (void*)&sf, (void*)&cfgv, (void*)&scalars,
                       (void*)&gscale, (void*)&gscale_dev, (void*)&g_sf, (void*)&g_depth_2, (void*)&Hh, (void*)&Ww, (void*)&slot,
                       (void*)&b0v, (void*)&nb, (void*)&tpp};
-      DVD_CUDA_CALL(cudaLaunchKernel(L.fn, dim3((unsigned)gx), dim3(kThreads + 32), args, (size_t)smem, st));
-    }
-    return 0;
-  }
-  if (packed && vecp >= 2) {
-    const int ipp = H * W / vecp;
-    dim3 g = vecp == 4 ? grid_for(reproject_loss_bwd_f2_kernel<2>, B, ipp) : grid_for(reproject_loss_bwd_f2_kernel<1>, B, ipp);
-    for (int b0 = 0; b0 < B; b0 += kPosePairs) {
-      const int nb = B - b0 < kPosePairs ? B - b0 : kPosePairs;
-      int slot = 0;
-      if (int e = stage_poses(poses, b0, nb, st, &slot)) return e;
-      dim3 gc(g.x, (unsigned)nb, 1);
-      if (vecp == 4) reproject_loss_bwd_f2_kernel<2><<<gc, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W, slot, b0);
-      else reproject_loss_bwd_f2_kernel<1><<<gc, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W, slot, b0);
-      DVD_CUDA_LAUNCH_CHECK("reproject_loss_bwd_f2");
+      DVD_CUDA_CALL(cudaLaunchKernel(fn, dim3((unsigned)gx), dim3(kThreads + 32), args, (size_t)smem, st));
     }
     return 0;
   }

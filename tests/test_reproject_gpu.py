@@ -108,6 +108,40 @@ def test_fused_matches_oracle_on_seeded_inputs(shape):
         assert rel_err(out[k], r_o[k]) < 1e-4, k
 
 
+@pytest.mark.parametrize('case', [(4, 224, 384, 3.0, 'joint_disp'), (4, 224, 384, 14.0, 'joint_sf'),
+                                  (5, 203, 384, 9.0, 'warm_disp'), (4, 224, 384, 40.0, 'joint_ratio_nomidas')])
+def test_packed_staged_path_matches_oracle(case):
+    """Shapes large enough for the packed-FP32 kernels (FFMA2 math, constant-bank poses, bulk-async staged inputs,
+    8-byte vector reductions for the scatter). Small and very large flows (border clamps), H = 203 leaves a ragged
+    last tile; every loss mode of the reference is covered (smf.py:285-324,140-150)."""
+    from dvd_b200 import ops, synthetic
+    from oracle import geometry
+    B, H, W, sigma, mode = case
+    kw = {'joint_disp': dict(midas=True, warm=False, use_disp=True, use_disp_ratio=False),
+          'warm_disp': dict(midas=True, warm=True, use_disp=True, use_disp_ratio=False),
+          'joint_sf': dict(midas=True, warm=False, use_disp=False, use_disp_ratio=False),
+          'joint_ratio_nomidas': dict(midas=False, warm=False, use_disp=False, use_disp_ratio=True)}[mode]
+    kw.update(flow_mul=1.0, disp_mul=0.7)
+    pairs = [(3 * k, 3 * k + 1 + (k % 4)) for k in range(B)]
+    batch = synthetic.make_batch(pairs, H=H, W=W, seed=11 + B, leading_dim=False, flow_sigma=sigma)
+    d1 = synthetic.make_depths(B, H, W, seed=1)
+    d2 = synthetic.make_depths(B, H, W, seed=2)
+    sf = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(7)) * 0.05
+    b64 = {k: (v.double() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    d1o, d2o, sfo = (t.double().requires_grad_() for t in (d1, d2, sf))
+    loss_o, parts_o, _ = geometry.reproject_and_loss(d1o, d2o, sfo, b64, **kw)
+    go = torch.autograd.grad(loss_o, [d1o, d2o, sfo])
+    b = _dev(batch)
+    poses = ops.pack_poses_from_batch(b)
+    d1g, d2g, sfg = (t.cuda().requires_grad_() for t in (d1, d2, sf))
+    mask = b['mask_2'].reshape(B, H, W).contiguous()
+    loss, scal = ops.reproject_loss(d1g, d2g, sfg, b['flow_1_2'], mask, poses, _cfg(kw))
+    assert abs(loss.item() - float(loss_o)) <= 1e-4 * abs(float(loss_o))
+    loss.backward()
+    for mine, ref, name in ((d1g.grad, go[0], 'g_d1'), (d2g.grad, go[1], 'g_d2'), (sfg.grad, go[2], 'g_sf')):
+        assert rel_err(mine, ref) < 2e-4, name
+
+
 def test_border_and_empty_mask_edge_cases():
     """Flow pushing every sample out of the image (border clamp) and an all-zero mask (N = 1e-8)."""
     from dvd_b200 import ops, synthetic

@@ -4,7 +4,7 @@
 tag=$1; shift
 mkdir -p gpurun_out
 env "$@" ncu --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed \
-  -k regex:'reproject_loss' -c 26 --csv --log-file gpurun_out/ncu_reproject_$tag.csv python tools/bench_reproject.py 64 $SMOOTH > gpurun_out/ncu_reproject_$tag.log 2>&1
+  -k regex:'reproject_(loss|rows)' -c 26 --csv --log-file gpurun_out/ncu_reproject_$tag.csv python tools/bench_reproject.py 64 $SMOOTH > gpurun_out/ncu_reproject_$tag.log 2>&1
 python - "$tag" <<'PY'
 import csv,sys,collections
 tag=sys.argv[1]
