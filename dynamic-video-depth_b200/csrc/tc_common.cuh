@@ -36,11 +36,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU. The bound is wall-clock
+// (about 2 s of SM cycles), not a spin count: one mbarrier.try_wait may itself suspend the thread for a system-dependent
+// time, so a count of polls says nothing about how long a dead wait lasts.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 23)) {
+    if (clock64() - t0 > 4000000000LL) {
       printf("dvd_b200: mbarrier wait timeout (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x,
              (void*)bar, parity);
       __trap();

@@ -442,6 +442,50 @@ def bn_act(x, bn, res=None, relu=True):
     return BnAct.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, relu)
 
 
+_CONV_DEBUG = bool(int(__import__('os').environ.get('DVD_CONV_DEBUG', '0')))
+
+
+def pack_conv_weight(weight, dgrad=False):
+    """weight [Cout,Cin,k,k] (any strides: contiguous or channels-last storage) -> the tap-major, TF32-rounded image
+    dvd_conv_nhwc_fwd streams with TMA: [k*k][Cout][Cin]; dgrad=True gives the data-gradient image
+    [k*k rotated by 180 degrees][Cin][Cout] (the adjoint of a stride-1 'same' convolution is a convolution with it)."""
+    co, ci, kh, kw = weight.shape
+    if kh != kw or weight.dtype != torch.float32 or not weight.is_cuda:
+        raise ValueError('pack_conv_weight needs a square float32 CUDA kernel')
+    out = torch.empty((kh * kw, ci, co) if dgrad else (kh * kw, co, ci), dtype=torch.float32, device=weight.device)
+    st = weight.stride()
+    lib = _lib.load()
+    LAUNCHES['n'] += 1
+    _lib.check(lib.dvd_conv_pack_weight(_ptr(weight), st[0], st[1], st[2], st[3], _ptr(out), co, ci, kh, int(bool(dgrad)),
+                                        _stream()), 'dvd_conv_pack_weight')
+    return out
+
+
+def conv_nhwc_fwd(x, w_tkc, ksize, bias=None, bn=None, res=None, relu=False):
+    """tcgen05 TF32 convolution (stride 1, dense, 'same' padding for ksize 3) on a channels-last tensor x [N,C,H,W]
+    (memory NHWC): y = act(BN(conv(x, w) + bias) + res); `bn` = (gamma, beta, running_mean, running_var, eps) of an
+    eval-mode BatchNorm2d or None. Returns a channels-last [N,Cout,H,W] tensor. Forward only (no autograd graph)."""
+    x = _as_cl(x)
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise ValueError('conv_nhwc_fwd needs float32 CUDA tensors')
+    N, C, H, W = x.shape
+    taps, cout, cin = w_tkc.shape
+    if taps != ksize * ksize or cin != C:
+        raise ValueError('packed weight %s does not match ksize=%d, Cin=%d' % (tuple(w_tkc.shape), ksize, C))
+    r = _as_cl(res) if res is not None else None
+    g, b, m, v, eps = bn if bn is not None else (None, None, None, None, 0.0)
+    y = torch.empty((N, cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    lib = _lib.load()
+    LAUNCHES['n'] += 1
+    if _CONV_DEBUG:
+        torch.cuda.synchronize()
+        print('conv_nhwc_fwd N=%d H=%d W=%d Cin=%d Cout=%d k=%d bias=%s bn=%s res=%s relu=%s' % (
+            N, H, W, C, cout, ksize, bias is not None, bn is not None, res is not None, relu), flush=True)
+    _lib.check(lib.dvd_conv_nhwc_fwd(_ptr(x), _ptr(w_tkc), _ptr(bias), _ptr(g), _ptr(b), _ptr(m), _ptr(v), float(eps), _ptr(r),
+                                     _ptr(y), N, H, W, C, cout, int(ksize), int(bool(relu)), _stream()), 'dvd_conv_nhwc_fwd')
+    return y
+
+
 class Upsample2x(torch.autograd.Function):
     """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=...) on channels-last tensors."""
 
