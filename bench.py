@@ -279,6 +279,33 @@ def roofline_mlp(tflops_peak, peak_kind, pairs=2, n_eval=2):
             'train_fwd_tflops': flops / t_trn / 1e12, 'bwd_dgrad_plus_wgrad_tflops': 2 * flops / t_bwd / 1e12}
 
 
+def roofline_conv(tflops_peak, peak_kind, images=16):
+    """tcgen05 TF32 convolution kernel (csrc/conv_tc.cu) on the largest dense MiDaS layer shape (3x3, 256 -> 256 at
+    96x56), CUDA events over back-to-back launches. TF32 dense peak = measured bf16 peak / 2 (B200_PROFILING.md ratio).
+    The kernel is NOT on the training path this round: reported for the record, not part of `value`."""
+    import torch
+    from dvd_b200 import ops
+    Hc, Wc, C = 56, 96, 256
+    x = torch.randn(images, C, Hc, Wc, device='cuda').contiguous(memory_format=torch.channels_last)
+    w = torch.randn(C, C, 3, 3, device='cuda') / 48.0
+    wp = ops.pack_conv_weight(w)
+    for _ in range(3):
+        ops.conv_nhwc_fwd(x, wp, 3)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(20_000_000)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        ops.conv_nhwc_fwd(x, wp, 3)
+    b.record()
+    torch.cuda.synchronize()
+    t = a.elapsed_time(b) * 1e-3 / 10
+    tf = 2.0 * images * Hc * Wc * C * C * 9 / t / 1e12
+    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel (3x3 256->256 @96x56, %d images, TF32)' % images, 'achieved': tf,
+            'unit': 'TFLOP/s', 'peak': tflops_peak / 2, 'peak_kind': peak_kind + ' dense bf16 (cuBLAS) / 2', 'frac': tf / (tflops_peak / 2),
+            'us': t * 1e6, 'on_training_path': False}
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -358,6 +385,7 @@ def run_b200_arm(args):
     hbm_peak, tflops_peak, peak_kind = measured_peaks()
     roof = roofline_reproject(args.roofline_pairs, hbm_peak, peak_kind)
     roof_mlp = roofline_mlp(tflops_peak, peak_kind)
+    roof_conv = roofline_conv(tflops_peak, peak_kind)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_steps(2, 0)   # bounded sample: ~20-30 s of CPU work
@@ -379,6 +407,7 @@ def run_b200_arm(args):
         'gpu_launches': launches,
         'roofline': roof,
         'roofline_mlp': roof_mlp,
+        'roofline_conv': roof_conv,
         'cpu_baseline': cpu,
         'last_batch_log': {k: v for k, v in logs[-1].items() if isinstance(v, (int, float))},
     }
