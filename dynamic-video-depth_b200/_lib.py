@@ -56,6 +56,7 @@ SIGNATURES = {
     'dvd_upsample2x_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'dvd_upsample2x_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'dvd_conv_pack_weight': [_P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _I, _I, _I, _I, _P],
+    'dvd_conv_nhwc_wgrad': [_P, _P, _P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _I, _I, _I, _I, _I, _I, _P],
     'dvd_conv_nhwc_fwd': [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'dvd_last_error': ctypes.c_char_p, 'dvd_mlp_packed_weights_bytes': ctypes.c_size_t,

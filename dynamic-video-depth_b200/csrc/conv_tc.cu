@@ -305,6 +305,146 @@ __global__ void __launch_bounds__(256) conv_pack_weight_kernel(const float* __re
   }
 }
 
+// =============================================================================================================
+// Weight gradient:  dW[t][co][ci] += sum over pixels  dY[px, co] * X[px + offset(t), ci]
+// GEMM with K = pixels: both operands are "MN-major" (their M / N index - the channel - is the contiguous one), which
+// tcgen05 accepts for TF32. A 64-pixel TMA box {32 ch, TW, TH, 1} lands as 64 rows of 128 bytes, SWIZZLE_128B = one
+// MN-atom column of the canonical MN-major image (8-row K groups 1024 B apart = SBO, next 32 channels one box = 8 KB
+// further = LBO); one MMA consumes 8 pixels (K = 8), i.e. +1024 B on both descriptors. The spatial shift of the tap is
+// again just the TMA coordinate of the X box (zero fill = padding). Split-K over pixel tiles across CTAs, partial sums
+// leave through fp32 reductions (vector red.global.add.v4 when the destination's Cin stride is 1).
+// Operands are NOT re-rounded here (both are activations): the tensor core truncates them to TF32, a uniform -7e-4
+// scale on dW (see the forward kernel) that Adam's normalisation cancels; tolerance of the test is 2e-3.
+constexpr int kWgStages = 2;
+constexpr int kWgPx = 64;                         // pixels (K) per stage
+constexpr int kWgBox = kWgPx * 128;               // bytes of one {32 ch, 64 px} box
+constexpr int kWgStageBytes = (4 + 8) * kWgBox;   // A: 128 out-channels, B: up to 256 in-channels
+constexpr size_t kWgSmem = 1024 + (size_t)kWgStages * kWgStageBytes + 256;
+
+struct WgradParams {
+  float* dw;                       // destination, element strides below
+  long s_co, s_ci, s_ky, s_kx;
+  int N, H, W, Cin, Cout, taps;
+  int TW, TH, tiles_w, tiles_h;    // 64-pixel tiles
+  int NT;                          // in-channels per output tile
+  int ksplit;                      // CTAs sharing one output tile
+};
+
+// MN-major operand of 32-bit elements: SWIZZLE_128B_BASE32B image (UMMA LayoutType 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+// 128-byte rows (32 channels) per K index, 32-byte chunk c of row r stored at chunk (c ^ (r & 3)), K atoms of 4 rows
+// 512 B apart (SBO), next 32 channels `lbo_bytes` further (LBO).
+__device__ __forceinline__ uint64_t make_sdesc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);   // A and B MN-major
+}
+
+__global__ void __launch_bounds__(192, 1) conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapDY,
+                                                             const __grid_constant__ CUtensorMap mapX,
+                                                             const __grid_constant__ WgradParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)kWgStages * kWgStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgStages;
+  uint64_t* acc_full = bars + 2 * kWgStages;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 256);
+  } else if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+
+  // this CTA: output tile (tap, 128 out-channels, NT in-channels) and a contiguous range of pixel tiles
+  const int out_tile = blockIdx.x / P.ksplit, part = blockIdx.x - out_tile * P.ksplit;
+  const int n_ci = P.Cin / P.NT, n_co = P.Cout / 128;
+  const int t = out_tile / (n_co * n_ci);
+  const int rem = out_tile - t * (n_co * n_ci);
+  const int m0 = (rem / n_ci) * 128, n0 = (rem % n_ci) * P.NT;
+  const int dy = P.taps == 9 ? t / 3 - 1 : 0, dx = P.taps == 9 ? t % 3 - 1 : 0;
+  const int px_tiles = P.N * P.tiles_h * P.tiles_w;
+  const int per = (px_tiles + P.ksplit - 1) / P.ksplit;
+  const int kt0 = part * per, kt1 = min(px_tiles, kt0 + per);
+  const int nb = P.NT / 32;
+  const uint32_t stage_tx = (uint32_t)(4 + nb) * kWgBox;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int kt = kt0; kt < kt1; ++kt, ++it) {
+        const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
+        const int img = kt / (P.tiles_h * P.tiles_w), r = kt - img * (P.tiles_h * P.tiles_w);
+        const int h0 = (r / P.tiles_w) * P.TH, w0 = (r % P.tiles_w) * P.TW;
+        uint8_t* st = base + (size_t)s * kWgStageBytes;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], stage_tx);
+        for (int j = 0; j < 4; ++j) tma_load_4d(st + j * kWgBox, &mapDY, m0 + 32 * j, w0, h0, img, &full[s]);
+        for (int j = 0; j < nb; ++j) tma_load_4d(st + (4 + j) * kWgBox, &mapX, n0 + 32 * j, w0 + dx, h0 + dy, img, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_mn(128, P.NT);
+      uint32_t it = 0;
+      for (int kt = kt0; kt < kt1; ++kt, ++it) {
+        const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(base + (size_t)s * kWgStageBytes), sb = sa + 4 * kWgBox;
+#pragma unroll
+        for (int ks = 0; ks < kWgPx / 8; ++ks)
+          umma_ss_tf32(tmem, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox), make_sdesc_mn_sw128_32b(sb + ks * 1024, kWgBox), idesc,
+                       (it | ks) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (kt1 > kt0) {
+    // epilogue: accumulator row = out-channel, columns = in-channels of this tile
+    const int q = warp & 3;
+    const int co = m0 + q * 32 + lane;
+    const uint32_t d = tmem + ((uint32_t)(q * 32) << 16);
+    float* dst = P.dw + (long)co * P.s_co + (long)(dy + (P.taps == 9 ? 1 : 0)) * P.s_ky + (long)(dx + (P.taps == 9 ? 1 : 0)) * P.s_kx;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < P.NT; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(d + c0, r);
+      tmem_ld_wait();
+      if (P.s_ci == 1 && ((reinterpret_cast<uintptr_t>(dst + n0 + c0) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + n0 + c0 + j), "f"(__uint_as_float(r[j])),
+                       "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(dst + (long)(n0 + c0 + j) * P.s_ci, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 // ---- host ----------------------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
@@ -319,12 +459,12 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 
 int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box) {
+             const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   auto fn = encode_fn();
   DVD_ARG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, ones,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DVD_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
   return 0;
@@ -401,5 +541,60 @@ extern "C" int dvd_conv_pack_weight(const float* weight, long stride_co, long st
   conv_pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(weight, stride_co, stride_ci, stride_ky, stride_kx, w_tkc,
                                                                   Cout, Cin, ksize, dgrad);
   DVD_CUDA_LAUNCH_CHECK("conv_pack_weight_kernel");
+  return 0;
+}
+
+extern "C" int dvd_conv_nhwc_wgrad(const float* x, const float* gy, float* dweight, long stride_co, long stride_ci, long stride_ky,
+                                   long stride_kx, int N, int H, int W, int Cin, int Cout, int ksize, void* stream) {
+  DVD_ARG_CHECK(x && gy && dweight, "null pointer");
+  DVD_ARG_CHECK(N >= 1 && H >= 1 && W >= 1, "bad shape N=%d H=%d W=%d", N, H, W);
+  DVD_ARG_CHECK(ksize == 1 || ksize == 3, "ksize must be 1 or 3 (stride 1, dense)");
+  if (Cin % 32 != 0 || Cout % 128 != 0 || (Cin > 256 && Cin % 256 != 0)) {
+    set_error("dvd_conv_nhwc_wgrad: needs Cout %% 128 == 0 and Cin %% 32 == 0 (<= 256 or a multiple of 256); Cin=%d Cout=%d", Cin, Cout);
+    return -2;
+  }
+  DVD_ARG_CHECK(aligned16(x) && aligned16(gy), "tensors must be 16-byte aligned");
+  WgradParams P{};
+  P.dw = dweight; P.s_co = stride_co; P.s_ci = stride_ci; P.s_ky = stride_ky; P.s_kx = stride_kx;
+  P.N = N; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout; P.taps = ksize * ksize;
+  P.NT = Cin >= 256 ? 256 : Cin;
+  if (ksize == 1) {
+    const long Pn = (long)N * H * W;
+    DVD_ARG_CHECK(Pn < (1L << 31), "too many pixels");
+    P.N = 1; P.H = 1; P.W = (int)Pn; P.TW = kWgPx; P.TH = 1;
+  } else {
+    long best = -1;
+    for (int tw = kWgPx; tw >= 8; tw >>= 1) {
+      const int th = kWgPx / tw;
+      const long padded = (long)((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th);
+      if (best < 0 || padded < best) { best = padded; P.TW = tw; P.TH = th; }
+    }
+  }
+  P.tiles_w = (P.W + P.TW - 1) / P.TW;
+  P.tiles_h = (P.H + P.TH - 1) / P.TH;
+  const int out_tiles = P.taps * (Cout / 128) * (Cin / P.NT);
+  const int px_tiles = P.N * P.tiles_h * P.tiles_w;
+  int ksplit = (num_sms() + out_tiles - 1) / out_tiles;
+  if (ksplit > px_tiles) ksplit = px_tiles;
+  if (ksplit < 1) ksplit = 1;
+  P.ksplit = ksplit;
+  CUtensorMap mapDY, mapX;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)P.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)P.W * Cout * 4, (cuuint64_t)P.H * P.W * Cout * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)P.TW, (cuuint32_t)P.TH, 1};
+    if (int e = make_map(&mapDY, gy, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  }
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)P.W, (cuuint64_t)P.H, (cuuint64_t)P.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)P.W * Cin * 4, (cuuint64_t)P.H * P.W * Cin * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)P.TW, (cuuint32_t)P.TH, 1};
+    if (int e = make_map(&mapX, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  }
+  static const bool attr_ok =
+      cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem) == cudaSuccess;
+  DVD_ARG_CHECK(attr_ok, "cudaFuncSetAttribute(conv_wgrad_tc_kernel) failed");
+  conv_wgrad_tc_kernel<<<out_tiles * ksplit, 192, kWgSmem, (cudaStream_t)stream>>>(mapDY, mapX, P);
+  DVD_CUDA_LAUNCH_CHECK("conv_wgrad_tc_kernel");
   return 0;
 }

@@ -486,6 +486,23 @@ def conv_nhwc_fwd(x, w_tkc, ksize, bias=None, bn=None, res=None, relu=False):
     return y
 
 
+def conv_nhwc_wgrad(x, gy, dweight):
+    """dweight[co,ci,ky,kx] += sum_px gy[px,co] * x[px + (ky-1,kx-1), ci] on the tcgen05 TF32 kernel (stride 1, dense,
+    'same' padding). x, gy: channels-last [N,C,H,W]; dweight: fp32 CUDA tensor [Cout,Cin,k,k] with any strides
+    (accumulated in place - zero it first for a plain gradient)."""
+    x, gy = _as_cl(x), _as_cl(gy)
+    N, C, H, W = x.shape
+    co, ci, kh, kw = dweight.shape
+    if gy.shape != (N, co, H, W) or ci != C or kh != kw:
+        raise ValueError('shape mismatch: x %s gy %s dweight %s' % (tuple(x.shape), tuple(gy.shape), tuple(dweight.shape)))
+    st = dweight.stride()
+    lib = _lib.load()
+    LAUNCHES['n'] += 1
+    _lib.check(lib.dvd_conv_nhwc_wgrad(_ptr(x), _ptr(gy), _ptr(dweight), st[0], st[1], st[2], st[3], N, H, W, C, co, kh,
+                                       _stream()), 'dvd_conv_nhwc_wgrad')
+    return dweight
+
+
 class Upsample2x(torch.autograd.Function):
     """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=...) on channels-last tensors."""
 

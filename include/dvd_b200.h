@@ -207,6 +207,13 @@ int dvd_conv_nhwc_fwd(const float* x, const float* w_tkc, const float* bias, con
 int dvd_conv_pack_weight(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx,
                          float* w_tkc, int Cout, int Cin, int ksize, int dgrad, void* stream);
 
+/* weight gradient of the same convolutions: dweight[co,ci,ky,kx] += sum_px gy[px,co] * x[px + (ky-1,kx-1), ci]  (ACCUMULATES
+ * with fp32 reductions into the caller's gradient buffer, addressed with the given element strides - contiguous or
+ * channels-last parameter storage). x [N,H,W,Cin], gy [N,H,W,Cout] NHWC fp32, TF32 tensor cores. Needs Cout % 128 == 0 and
+ * Cin % 32 == 0 (Cin <= 256 or a multiple of 256): returns -2 otherwise. Replaces cuDNN's convolution_backward weight path.  */
+int dvd_conv_nhwc_wgrad(const float* x, const float* gy, float* dweight, long stride_co, long stride_ci, long stride_ky,
+                        long stride_kx, int N, int H, int W, int Cin, int Cout, int ksize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

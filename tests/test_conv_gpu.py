@@ -77,3 +77,35 @@ def test_unsupported_shapes_fail_loudly():
     w = torch.randn(32, 3, 3, 3).cuda()
     with pytest.raises(RuntimeError):
         ops.conv_nhwc_fwd(x, ops.pack_conv_weight(w), 3)
+
+
+WGRAD_CASES = [
+    # N, H,  W,  Cin,  Cout, k, channels_last weight gradient
+    (2, 28, 48, 64, 128, 3, False),
+    (1, 56, 96, 256, 256, 3, True),      # 16-byte vector reductions (Cin stride 1)
+    (3, 7, 12, 1024, 256, 1, True),      # 1x1: K = 252 pixels (ragged), four in-channel tiles
+    (1, 30, 50, 32, 128, 3, False),      # ragged spatial tiles, N = 32
+    (2, 14, 24, 512, 128, 1, False),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_conv_wgrad_matches_torch_fp64(case):
+    """dvd_conv_nhwc_wgrad (both operands MN-major TF32, split-K, fp32 reductions) vs torch.nn.grad.conv2d_weight in
+    fp64. The operands are activations and are not re-rounded, so the tensor core's TF32 truncation leaves a uniform
+    -7e-4 scale on the result (csrc/conv_tc.cu): tolerance 2e-3; the call accumulates into its destination."""
+    from dvd_b200 import ops
+    N, H, W, ci, co, k, cl = case
+    g = torch.Generator().manual_seed(77 + ci + co + H)
+    x = torch.randn(N, ci, H, W, generator=g)
+    gy = torch.randn(N, co, H, W, generator=g)
+    ref = torch.nn.grad.conv2d_weight(x.double(), (co, ci, k, k), gy.double(), padding=k // 2)
+    dw = torch.zeros(co, ci, k, k, device='cuda')
+    if cl:
+        dw = dw.contiguous(memory_format=torch.channels_last)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last)
+    gc = gy.cuda().contiguous(memory_format=torch.channels_last)
+    ops.conv_nhwc_wgrad(xc, gc, dw)
+    assert rel_err(dw, ref) < 2e-3
+    ops.conv_nhwc_wgrad(xc, gc, dw)          # accumulates
+    assert rel_err(dw, 2 * ref) < 2e-3
