@@ -39,6 +39,8 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--roofline-pairs', type=int, default=64)
+    ap.add_argument('--conv-probe', nargs=2, metavar=('TFLOPS_PEAK', 'PEAK_KIND'), default=None,
+                    help='internal: measure the tcgen05 convolution kernel, print its roofline dict as JSON and exit')
     return ap.parse_args()
 
 
@@ -306,6 +308,25 @@ def roofline_conv(tflops_peak, peak_kind, images=16):
             'us': t * 1e6, 'on_training_path': False}
 
 
+def conv_probe_subprocess(tflops_peak, peak_kind, limit_s=120):
+    import subprocess
+    env = dict(os.environ)
+    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT'):   # a plain single-GPU child
+        env.pop(k, None)
+    env.setdefault('CUDA_VISIBLE_DEVICES', os.environ.get('CUDA_VISIBLE_DEVICES', '0').split(',')[0])
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--conv-probe', repr(float(tflops_peak)), str(peak_kind)],
+                             capture_output=True, text=True, timeout=limit_s, env=env)
+        lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith('{')]
+        if out.returncode != 0 or not lines:
+            return {'error': 'conv probe rc=%d: %s' % (out.returncode, (out.stderr or out.stdout)[-300:])}
+        return json.loads(lines[-1])
+    except subprocess.TimeoutExpired:
+        return {'error': 'conv probe exceeded %d s' % limit_s}
+    except Exception as e:   # noqa: BLE001
+        return {'error': repr(e)[:300]}
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -388,11 +409,10 @@ def run_b200_arm(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_steps(2, 0)   # bounded sample: ~20-30 s of CPU work
-    # last GPU section, and not allowed to take the line down: the convolution kernel is not on the measured path
-    try:
-        roof_conv = roofline_conv(tflops_peak, peak_kind)
-    except Exception as e:   # noqa: BLE001
-        roof_conv = {'error': repr(e)[:300]}
+    # last GPU section, and not allowed to take the line down (the convolution kernel is not on the measured path):
+    # it runs in a child process with a hard time limit, so neither an exception nor a device fault nor a stall there
+    # can reach this process's CUDA context or delay the JSON line by more than the limit
+    roof_conv = conv_probe_subprocess(tflops_peak, peak_kind)
     pairs_total = K * B * world
     line = {
         'metric': METRIC, 'value': pairs_total / t_dev, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
@@ -422,6 +442,11 @@ def run_b200_arm(args):
 
 def main():
     args = parse()
+    if args.conv_probe is not None:
+        import torch
+        torch.cuda.set_device(0)
+        print(json.dumps(roofline_conv(float(args.conv_probe[0]), args.conv_probe[1])), flush=True)
+        return
     if args.impl == 'reference':
         run_reference_arm(args)
     else:
