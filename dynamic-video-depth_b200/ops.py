@@ -503,6 +503,49 @@ def conv_nhwc_wgrad(x, gy, dweight):
     return dweight
 
 
+def conv_tc_supported(cin, cout, k):
+    """Shapes all three tcgen05 convolution kernels accept (forward, data gradient = forward kernel with the roles of the
+    channel counts swapped, weight gradient)."""
+    fwd = cin % 32 == 0 and cout % 16 == 0 and (cout <= 256 or cout % 256 == 0)
+    dgrad = cout % 32 == 0 and cin % 16 == 0 and (cin <= 256 or cin % 256 == 0)
+    wgrad = cout % 128 == 0 and cin % 32 == 0 and (cin <= 256 or cin % 256 == 0)
+    return k in (1, 3) and fwd and dgrad and wgrad
+
+
+class ConvTc(torch.autograd.Function):
+    """Dense stride-1 'same' convolution (+ bias) with all three passes on the tcgen05 TF32 kernels of csrc/conv_tc.cu.
+    STAGED FOR ROUND 2: the three kernels are parity-tested one by one (tests/test_conv_gpu.py); this Function and its use
+    in the MiDaS mirror (DVD_CONV_TC_TRAIN=1) were written after the round's GPU budget was spent and have not run on a
+    GPU yet - tests/test_zz_conv_train_gpu.py is their (equally opt-in) test.
+    forward(x channels-last [N,Cin,H,W], weight [Cout,Cin,k,k], bias|None) -> y channels-last [N,Cout,H,W]"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = _as_cl(x)
+        y = conv_nhwc_fwd(x, pack_conv_weight(weight), weight.shape[2], bias)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = _as_cl(gy)
+        k = weight.shape[2]
+        gx = conv_nhwc_fwd(gy, pack_conv_weight(weight, dgrad=True), k) if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            # like BnAct: accumulate straight into an existing .grad (the flat gradient buffer, zeroed once per step) and
+            # hand autograd None for it; otherwise return a fresh gradient with the weight's own strides
+            if weight.grad is not None and weight.grad.dtype == torch.float32 and weight.grad.is_cuda:
+                conv_nhwc_wgrad(x, gy, weight.grad)
+            else:
+                gw = torch.zeros_like(weight)
+                conv_nhwc_wgrad(x, gy, gw)
+        gb = gy.sum(dim=(0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb
+
+
 class Upsample2x(torch.autograd.Function):
     """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=...) on channels-last tensors."""
 
