@@ -4,13 +4,14 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs B] [--impl b200|reference]
 
 One "step" = one joint-phase optimisation step (depth net + scene-flow MLP trainable, flags of
-experiments/davis/train_sequence.sh) over B synthetic frame pairs of 384x224 per GPU (BASELINE.json
-configs[1]: fused re-projection kernels + PyTorch/cuDNN depth net; the scene-flow MLP runs on the tcgen05
-kernels). Gaps cycle through {1,2,4,6,8} step by step (all pairs of one step share the gap).
-Prints ONE JSON line (rank 0). See the repository README / DESIGN.md for the field meanings.
+experiments/davis/train_sequence.sh) over B synthetic frame pairs per GPU (default 384x224, 80 frames =
+BASELINE.json configs[2]: the full sm_100a path - tcgen05 depth CNN + tcgen05 scene-flow MLP + fused re-projection
+kernels; --height/--width/--frames/--gaps select the other configs). Gaps cycle step by step (all pairs of one
+step share the gap). Prints ONE JSON line (rank 0). See the repository README / DESIGN.md for the field meanings.
 
 --impl reference : the reference's CPU PyTorch computation, restated by oracle/step.py (kind "port" — the
-Python reference tree cannot travel to the GPU box), on the host cores, one pair per step.
+Python reference tree cannot travel to the GPU box), on the host cores; same workload and gap schedule, each step a
+bounded sample of it (one pair).
 """
 import argparse
 import json
@@ -30,6 +31,27 @@ METRIC = 'frame-pairs/sec per step (384x224)'
 UNIT = 'frame-pairs/s'
 
 
+def configure(args):
+    """--height/--width/--frames/--gaps -> module-level workload (BASELINE.json configs[2..4])."""
+    global H, W, N_FRAMES, GAPS, METRIC
+    H, W, N_FRAMES = args.height, args.width, args.frames
+    GAPS = tuple(int(g) for g in args.gaps.split(','))
+    METRIC = 'frame-pairs/sec per step (%dx%d)' % (W, H)
+
+
+def workload_name():
+    if (W, H, N_FRAMES) == (384, 224, 80):
+        base = "synthetic 80-frame sequence 384x224 (BASELINE.json configs[2]: full sm_100a path)"
+    elif (W, H, N_FRAMES) == (768, 448, 80):
+        base = "synthetic 80-frame sequence 768x448 (BASELINE.json configs[3])"
+    elif (W, H, N_FRAMES) == (512, 288, 200):
+        base = "ShutterStock-shape sequence 512x288, 200 frames, mixed-gap flow pairs (BASELINE.json configs[4], fp32/TF32 I/O)"
+    else:
+        base = "synthetic %d-frame sequence %dx%d" % (N_FRAMES, W, H)
+    return base + ("; joint phase (--midas --use_disp --time_dependent --acc_mul 1): tcgen05 TF32 MiDaS depth CNN fwd+bwd, "
+                   "tcgen05 bf16x3 scene-flow MLP, fused re-projection kernels, flat Adam; gaps cycle %s" % ','.join(map(str, GAPS)))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -37,10 +59,13 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--pairs', type=int, default=8, help='frame pairs per step per GPU')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--height', type=int, default=224)
+    ap.add_argument('--width', type=int, default=384)
+    ap.add_argument('--frames', type=int, default=80)
+    ap.add_argument('--gaps', type=str, default='8,6,4,2,1')
+    ap.add_argument('--no-extras', action='store_true', help='skip the B=1 line, the eager-GPU reference and the kernel rooflines')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--roofline-pairs', type=int, default=64)
-    ap.add_argument('--conv-probe', nargs=2, metavar=('TFLOPS_PEAK', 'PEAK_KIND'), default=None,
-                    help='internal: measure the tcgen05 convolution kernel, print its roofline dict as JSON and exit')
     return ap.parse_args()
 
 
@@ -98,12 +123,15 @@ class ClockSampler:
 
 
 def step_pairs(step, rank, world, B):
-    """Pairs of one step on one rank: all share the gap (uniform Euler-step count across ranks), disjoint
-    frame ids across ranks — the DistributedSampler-style partition of the pair list (train.py:301-305)."""
+    """Pairs of one step on one rank: all share the gap (uniform Euler-step count across ranks); the global batch of the
+    step is a run of world*B consecutive start frames (wrapping), of which rank r takes its B - disjoint across ranks
+    whenever world*B <= n_frames-1-gap. The product sampler is dvd_b200.datasets.resident.GapBucketSampler
+    (DistributedSampler-style partition of the pair list, train.py:301-305, bucketed by gap)."""
     gap = GAPS[step % len(GAPS)]
+    n = N_FRAMES - 1 - gap
     out = []
     for j in range(B):
-        f = (step * 7 + (rank * B + j) * 3) % (N_FRAMES - 1 - gap)
+        f = (step * 7 + rank * B + j) % n
         out.append((f, f + gap))
     return gap, out
 
@@ -132,16 +160,23 @@ def _pick_cpu_threads(depth_sd):
     return best, cores
 
 
-def cpu_reference_steps(n_steps, warmup, quiet=True):
-    """The reference's CPU path (oracle port): joint-phase step, 1 pair, gap 2, 384x224, host cores."""
-    import torch
+def _seeded_state():
     from dvd_b200 import synthetic
     from dvd_b200.networks.sceneflow_field import SceneFlowFieldNet
     from dvd_b200.third_party.MiDaS import MidasNet
-    from oracle import step as ostep
-    opt = synthetic.default_opt()
     depth = synthetic.seed_net_(MidasNet(non_negative=True, normalize_input=True), 0, 2000.0).state_dict()
     mlp = synthetic.seed_net_(SceneFlowFieldNet(net_width=256, n_layers=4, time_dependent=True, N_freq_xyz=16, N_freq_t=16), 1).state_dict()
+    return depth, mlp
+
+
+def cpu_reference_steps(n_steps, warmup, quiet=True):
+    """The reference's CPU path (oracle port): joint-phase step on the host cores, ONE pair per step (a bounded sample of
+    the GPU arm's step), gaps cycling through the same schedule as the GPU arm."""
+    import torch
+    from dvd_b200 import synthetic
+    from oracle import step as ostep
+    opt = synthetic.default_opt()
+    depth, mlp = _seeded_state()
     threads, cores = _pick_cpu_threads(depth)
     ad, am = {}, {}
     times = []
@@ -150,7 +185,9 @@ def cpu_reference_steps(n_steps, warmup, quiet=True):
     tiny = synthetic.make_batch([(3, 5)], H=64, W=96, n_frames=N_FRAMES, seed=99, leading_dim=False)
     ostep.train_step(depth, mlp, tiny, opt, epoch=6)
     for i in range(warmup + n_steps):
-        batch = synthetic.make_batch([(10 + i, 12 + i)], H=H, W=W, n_frames=N_FRAMES, seed=i, leading_dim=False)
+        gap = GAPS[i % len(GAPS)]
+        f = (10 + i) % (N_FRAMES - 1 - gap)
+        batch = synthetic.make_batch([(f, f + gap)], H=H, W=W, n_frames=N_FRAMES, seed=i, leading_dim=False)
         t0 = time.perf_counter()
         log, depth, mlp, _ = ostep.train_step(depth, mlp, batch, opt, epoch=6, adam_depth=ad, adam_mlp=am)
         dt = time.perf_counter() - t0
@@ -158,8 +195,9 @@ def cpu_reference_steps(n_steps, warmup, quiet=True):
             times.append(dt)
     total = sum(times)
     return {'value': len(times) / total, 'unit': UNIT, 'cores': threads, 'host_cores': cores, 'kind': 'port',
-            'sample': '%d joint-phase step(s) x 1 pair (gap 2) at %dx%d, oracle/step.py on torch CPU, %d threads '
-                      '(fastest of a sweep over 8..%d), %d warm-up' % (len(times), W, H, threads, cores, warmup),
+            'sample': '%d joint-phase step(s) x 1 pair at %dx%d, gaps cycling %s (the GPU arm\'s schedule), oracle/step.py on torch CPU, '
+                      '%d threads (fastest of a sweep over 8..%d), %d warm-up' % (len(times), W, H, ','.join(map(str, GAPS)), threads,
+                                                                                  cores, warmup),
             'seconds': total, 'last_loss': log['loss']}
 
 
@@ -171,12 +209,58 @@ def run_reference_arm(args):
     line = {'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * cb['seconds'] / max(args.steps, 1), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': "synthetic 80-frame sequence, 384x224 (BASELINE.json configs[0]/[1]), joint phase, "
-                                   "1 pair per step, CPU PyTorch path of the reference restated by oracle/step.py"},
+            'config': {'workload': workload_name(), 'pairs_per_step_per_gpu': args.pairs,
+                       'sampled_as': 'one pair per CPU step of the same gap schedule (bounded sample); CPU PyTorch path of the '
+                                     'reference restated by oracle/step.py'},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_reference(dev, B, n_steps=5, warmup=2):
+    """Denominator of the >=10x target: the reference-equivalent step in EAGER PyTorch on the same
+    GPU - oracle/step.py (the restatement of Model._train_on_batch the parity tests pin to the reference) with every tensor
+    on cuda:0 and torch's defaults (cuDNN TF32 convolutions on, as the reference would run today). Two workloads: the
+    reference's own schedule (1 pair per step, train_sequence.sh:29-34) and this bench's B pairs per step; same gap cycle."""
+    import torch
+    from dvd_b200 import synthetic
+    from oracle import step as ostep
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = False
+    opt = synthetic.default_opt()
+    depth, mlp = _seeded_state()
+    sd_d = {k: v.to(dev) for k, v in depth.items()}
+    sd_m = {k: v.to(dev) for k, v in mlp.items()}
+
+    def run(pairs_per_step):
+        bs = []
+        for i in range(warmup + n_steps):
+            gap = GAPS[i % len(GAPS)]
+            n = N_FRAMES - 1 - gap
+            pr = [((5 * i + j) % n, (5 * i + j) % n + gap) for j in range(pairs_per_step)]
+            b = synthetic.make_batch(pr, H=H, W=W, n_frames=N_FRAMES, seed=200 + i, leading_dim=False)
+            bs.append({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()})
+        ad, am = {}, {}
+        d, m = sd_d, sd_m
+        for i in range(warmup):
+            _, d, m, _ = ostep.train_step(d, m, bs[i], opt, 6, ad, am)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in bs[warmup:]:
+            _, d, m, _ = ostep.train_step(d, m, b, opt, 6, ad, am)
+        torch.cuda.synchronize()
+        return n_steps * pairs_per_step / (time.perf_counter() - t0)
+
+    out = {'what': 'oracle/step.py (reference-equivalent eager PyTorch step) on cuda:0, cuDNN TF32 (torch default), inputs resident, '
+                   '%d timed steps after %d warm-up, gaps cycling %s' % (n_steps, warmup, ','.join(map(str, GAPS))), 'unit': UNIT}
+    try:
+        out['pairs_per_step_1'] = run(1)
+        out['pairs_per_step_%d' % B] = run(B) if B > 1 else out['pairs_per_step_1']
+    except Exception as e:   # noqa: BLE001
+        out['error'] = repr(e)[:300]
+    torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -281,50 +365,42 @@ def roofline_mlp(tflops_peak, peak_kind, pairs=2, n_eval=2):
             'train_fwd_tflops': flops / t_trn / 1e12, 'bwd_dgrad_plus_wgrad_tflops': 2 * flops / t_bwd / 1e12}
 
 
-def roofline_conv(tflops_peak, peak_kind, images=16):
-    """tcgen05 TF32 convolution kernel (csrc/conv_tc.cu) on the largest dense MiDaS layer shape (3x3, 256 -> 256 at
-    96x56), CUDA events over back-to-back launches. TF32 dense peak = measured bf16 peak / 2 (B200_PROFILING.md ratio).
-    The kernel is NOT on the training path this round: reported for the record, not part of `value`."""
+def roofline_depth_convs(model, batch, epoch, tflops_peak, peak_kind):
+    """Live roofline of the tensor-core convolution kernels of the step (the kernels that dominate it): one more optimisation
+    step with every conv2d_tc / conv_wgrad launch bracketed by CUDA events on the launching stream (dvd_b200.conv_ops.PROFILE);
+    achieved = sum of algorithmic FLOPs / sum of launch durations per kernel; TF32 dense peak = measured bf16 peak / 2."""
     import torch
-    from dvd_b200 import ops
-    Hc, Wc, C = 56, 96, 256
-    x = torch.randn(images, C, Hc, Wc, device='cuda').contiguous(memory_format=torch.channels_last)
-    w = torch.randn(C, C, 3, 3, device='cuda') / 48.0
-    wp = ops.pack_conv_weight(w)
-    for _ in range(3):
-        ops.conv_nhwc_fwd(x, wp, 3)
-    torch.cuda.synchronize()
-    torch.cuda._sleep(20_000_000)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(10):
-        ops.conv_nhwc_fwd(x, wp, 3)
-    b.record()
-    torch.cuda.synchronize()
-    t = a.elapsed_time(b) * 1e-3 / 10
-    tf = 2.0 * images * Hc * Wc * C * C * 9 / t / 1e12
-    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel (3x3 256->256 @96x56, %d images, TF32)' % images, 'achieved': tf,
-            'unit': 'TFLOP/s', 'peak': tflops_peak / 2, 'peak_kind': peak_kind + ' dense bf16 (cuBLAS) / 2', 'frac': tf / (tflops_peak / 2),
-            'us': t * 1e6, 'on_training_path': False}
-
-
-def conv_probe_subprocess(tflops_peak, peak_kind, limit_s=120):
-    import subprocess
-    env = dict(os.environ)
-    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT'):   # a plain single-GPU child
-        env.pop(k, None)
-    env.setdefault('CUDA_VISIBLE_DEVICES', os.environ.get('CUDA_VISIBLE_DEVICES', '0').split(',')[0])
+    from dvd_b200 import conv_ops
+    conv_ops.PROFILE = []
     try:
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--conv-probe', repr(float(tflops_peak)), str(peak_kind)],
-                             capture_output=True, text=True, timeout=limit_s, env=env)
-        lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith('{')]
-        if out.returncode != 0 or not lines:
-            return {'error': 'conv probe rc=%d: %s' % (out.returncode, (out.stderr or out.stdout)[-300:])}
-        return json.loads(lines[-1])
-    except subprocess.TimeoutExpired:
-        return {'error': 'conv probe exceeded %d s' % limit_s}
-    except Exception as e:   # noqa: BLE001
-        return {'error': repr(e)[:300]}
+        model._train_on_batch(epoch, 0, batch)
+        torch.cuda.synchronize()
+        rec = conv_ops.PROFILE
+    finally:
+        conv_ops.PROFILE = None
+    agg = {}
+    for kind, flops, e0, e1 in rec:
+        a = agg.setdefault(kind, [0.0, 0.0, 0])
+        a[0] += flops
+        a[1] += e0.elapsed_time(e1) * 1e-3
+        a[2] += 1
+    peak = tflops_peak / 2
+    kern = {'fwd': 'conv2d_tc_kernel (forward)', 'dgrad': 'conv2d_tc_kernel (data gradient)', 'wgrad': 'conv_wgrad_kernel'}
+    parts = []
+    for k in ('fwd', 'dgrad', 'wgrad'):
+        if k in agg and agg[k][1] > 0:
+            f, t, n = agg[k]
+            parts.append({'kernel': kern[k], 'launches': n, 'gflop': f / 1e9, 'ms': t * 1e3, 'achieved': f / t / 1e12, 'frac': f / t / 1e12 / peak})
+    tot_f = sum(a[0] for a in agg.values())
+    tot_t = sum(a[1] for a in agg.values())
+    dom = max(parts, key=lambda q: q['ms']) if parts else None
+    return {'bound': 'tensor', 'kernel': dom['kernel'] if dom else None, 'achieved': dom['achieved'] if dom else None, 'peak': peak,
+            'unit': 'TFLOP/s', 'frac': dom['frac'] if dom else None, 'traffic': None, 'peak_kind': peak_kind + ' dense bf16 (cuBLAS) / 2 = TF32',
+            'how': 'CUDA events around every tensor-core convolution launch of one %d-pair step (MiDaS, %dx%d): algorithmic FLOPs '
+                   '(2*N*OH*OW*Cout*Cin/groups*k*k per pass) / event time, summed per kernel' % (batch['img_1'].shape[-4], W, H),
+            'all_conv_kernels': {'achieved': tot_f / tot_t / 1e12 if tot_t else None, 'frac': tot_f / tot_t / 1e12 / peak if tot_t else None,
+                                 'ms_per_step': tot_t * 1e3, 'gflop_per_step': tot_f / 1e9},
+            'kernels': parts}
 
 
 def run_b200_arm(args):
@@ -342,8 +418,6 @@ def run_b200_arm(args):
         dist.init_process_group('nccl', device_id=dev)
     from dvd_b200 import ops, synthetic
     from dvd_b200.models import get_model
-    torch.backends.cudnn.allow_tf32 = True         # the reference's own GPU default (torch): TF32 convolutions
-    torch.backends.cudnn.benchmark = os.environ.get('DVD_BENCH_CUDNN_BENCHMARK', '1') != '0'
     opt = synthetic.default_opt(batch_size=1, multiprocess_distributed=world > 1, global_rank=rank)
     model = get_model('scene_flow_motion_field')(opt, None)
     synthetic.seed_net_(model.net_depth, 0, 2000.0)
@@ -354,26 +428,26 @@ def run_b200_arm(args):
     B, K, Wm = args.pairs, args.steps, args.warmup
     EPOCH = opt.warm_sf + 1   # joint phase
 
-    def host_batch(step):
-        gap, pairs = step_pairs(step, rank, world, B)
-        b = synthetic.make_batch(pairs, H=H, W=W, n_frames=N_FRAMES, seed=1000 * rank + step)
-        return {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
-
-    total_steps = Wm + K
-    host = [host_batch(s) for s in range(total_steps)]
-    resident = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host]
-    for rb, hb in zip(resident, host):   # keep the scalar metadata readable on the host without a sync
-        rb['time_step'] = hb['time_step']
-        rb['steps_hint'] = int(round(float(hb['frame_id_2'].reshape(-1)[0] - hb['frame_id_1'].reshape(-1)[0])))
+    def make_batches(Bp, total_steps):
+        host = []
+        for s_ in range(total_steps):
+            gap, pairs = step_pairs(s_, rank, world, Bp)
+            b = synthetic.make_batch(pairs, H=H, W=W, n_frames=N_FRAMES, seed=1000 * rank + s_)
+            host.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()})
+        resident = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in hb.items()} for hb in host]
+        for rb, hb in zip(resident, host):   # keep the scalar metadata readable on the host without a sync
+            rb['time_step'] = hb['time_step']
+            rb['steps_hint'] = int(round(float(hb['frame_id_2'].reshape(-1)[0] - hb['frame_id_1'].reshape(-1)[0])))
+        return host, resident
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, sampler=None):
-        for s in range(Wm):
-            model._train_on_batch(EPOCH, s, batches[s])
+    def timed(batches, n_warm, n_steps, sampler=None):
+        for s_ in range(n_warm):
+            model._train_on_batch(EPOCH, s_, batches[s_])
         barrier()
         if sampler:
             sampler.start()
@@ -381,7 +455,7 @@ def run_b200_arm(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         torch.cuda.profiler.start()      # cudaProfilerStart: `ncu --profile-from-start off` lists exactly the timed launches
-        logs = [model._train_on_batch(EPOCH, Wm + s, batches[Wm + s]) for s in range(K)]
+        logs = [model._train_on_batch(EPOCH, n_warm + s_, batches[n_warm + s_]) for s_ in range(n_steps)]
         torch.cuda.profiler.stop()
         b.record()
         barrier()
@@ -393,45 +467,67 @@ def run_b200_arm(args):
             t = float(tt)
         return t, logs, clocks, ops.LAUNCHES['n']
 
+    host, resident = make_batches(B, Wm + K)
     # (1) device-resident inputs: the headline `value`
-    t_dev, logs, clocks, launches = timed(resident, ClockSampler(local))
+    t_dev, logs, clocks, launches = timed(resident, Wm, K, ClockSampler(local))
     # (2) end to end through the plug-in call with HOST (pinned) batches: H2D + D2H inside the timed region
-    t_e2e, logs2, _, _ = timed(host)
+    t_e2e, logs2, _, _ = timed(host, Wm, K)
     h2d = sum(v.numel() * v.element_size() for v in host[Wm].values() if torch.is_tensor(v))
     d2h = 9 * 4
+    # (3) the reference's own schedule: ONE pair per step (train_sequence.sh:29-34), same gap cycle
+    b1 = None
+    if not args.no_extras and B != 1:
+        K1 = max(K, 10)
+        host1, res1 = make_batches(1, Wm + K1)
+        t1_dev, _, _, l1 = timed(res1, Wm, K1)
+        t1_e2e, _, _, _ = timed(host1, Wm, K1)
+        b1 = {'value': K1 * world / t1_dev, 'unit': UNIT, 'ms_per_step': 1e3 * t1_dev / K1, 'steps': K1,
+              'e2e': K1 * world / t1_e2e, 'gpu_launches_per_step': l1 / K1,
+              'what': 'this arm at 1 pair per step per GPU (the batch the reference DataLoader delivers), same gap cycle'}
+        del host1, res1
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     hbm_peak, tflops_peak, peak_kind = measured_peaks()
-    roof = roofline_reproject(args.roofline_pairs, hbm_peak, peak_kind)
-    roof_mlp = roofline_mlp(tflops_peak, peak_kind)
+    pairs_total = K * B * world
+    value = pairs_total / t_dev
+    roof_conv = roof = roof_mlp = gref = None
+    if not args.no_extras:
+        roof_conv = roofline_depth_convs(model, resident[Wm], EPOCH, tflops_peak, peak_kind)
+        roof = roofline_reproject(args.roofline_pairs, hbm_peak, peak_kind)
+        roof_mlp = roofline_mlp(tflops_peak, peak_kind)
+        del host, resident
+        torch.cuda.empty_cache()
+        if world == 1:
+            gref = gpu_eager_reference(dev, B)
+            if 'pairs_per_step_%d' % B in gref:
+                gref['speedup_value_vs_eager_same_batch'] = value / gref['pairs_per_step_%d' % B]
+                gref['speedup_value_vs_eager_1_pair_per_step'] = value / gref['pairs_per_step_1']
+                if b1:
+                    gref['speedup_b1_vs_eager_1_pair_per_step'] = b1['value'] / gref['pairs_per_step_1']
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_steps(2, 0)   # bounded sample: ~20-30 s of CPU work
-    # last GPU section, and not allowed to take the line down (the convolution kernel is not on the measured path):
-    # it runs in a child process with a hard time limit, so neither an exception nor a device fault nor a stall there
-    # can reach this process's CUDA context or delay the JSON line by more than the limit
-    roof_conv = conv_probe_subprocess(tflops_peak, peak_kind)
-    pairs_total = K * B * world
+        cpu = cpu_reference_steps(len(GAPS), 0)   # bounded sample: one step per gap of the schedule, ~20-30 s of CPU work
     line = {
-        'metric': METRIC, 'value': pairs_total / t_dev, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
         'ms_per_step': 1e3 * t_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32 storage; MLP GEMMs bf16x3-split on tcgen05 (fp32-grade, err ~2e-5); re-projection fp32; depth-net convs cuDNN TF32 (torch default, = reference on GPU)',
+        'dtype': 'f32 storage; depth-CNN convolutions TF32 on tcgen05 (operands RN-rounded, fp32 accumulate = the reference\'s GPU default); '
+                 'MLP GEMMs bf16x3-split on tcgen05 (fp32-grade, err ~2e-5); re-projection, stem, head, Adam fp32',
         'data': 'synthetic',
-        'config': {'workload': "synthetic 80-frame sequence 384x224 (BASELINE.json configs[1]: DAVIS 'dog' shape, fused "
-                               "re-projection kernels + PyTorch/cuDNN MiDaS depth net + tcgen05 scene-flow MLP), joint phase "
-                               "(--midas --use_disp --time_dependent --acc_mul 1), gaps cycle 8,6,4,2,1",
+        'config': {'workload': workload_name(), 'height': H, 'width': W, 'frames': N_FRAMES, 'gaps': list(GAPS),
                    'pairs_per_step_per_gpu': B, 'global_pairs_per_step': B * world, 'parallelism': 'dp%d' % world,
-                   'l2': 'per-step working set (depth-net activations + %.1f GB saved MLP activations) >> 126 MB L2; no explicit flush' % (
-                       B * 4.4 * 0.504)},
+                   'l2': 'per-step working set (depth-net activations of %d images + saved MLP activations, several GB) >> 126 MB L2; '
+                         'no explicit flush' % (2 * B)},
         'clocks': clocks,
         'e2e': {'value': pairs_total / t_e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': 1e3 * t_e2e / K, 'api': 'Model._train_on_batch(epoch, i, pinned-host batch dict)'},
         'gpu_launches': launches,
-        'roofline': roof,
+        'b1': b1,
+        'gpu_reference': gref,
+        'roofline': roof_conv,
+        'roofline_reproject': roof,
         'roofline_mlp': roof_mlp,
-        'roofline_conv': roof_conv,
         'cpu_baseline': cpu,
         'last_batch_log': {k: v for k, v in logs[-1].items() if isinstance(v, (int, float))},
     }
@@ -442,11 +538,7 @@ def run_b200_arm(args):
 
 def main():
     args = parse()
-    if args.conv_probe is not None:
-        import torch
-        torch.cuda.set_device(0)
-        print(json.dumps(roofline_conv(float(args.conv_probe[0]), args.conv_probe[1])), flush=True)
-        return
+    configure(args)
     if args.impl == 'reference':
         run_reference_arm(args)
     else:

@@ -18,6 +18,20 @@ class LossCfg(ctypes.Structure):
                 ('second_is_disp', ctypes.c_int), ('flow_mul', ctypes.c_float), ('disp_mul', ctypes.c_float)]
 
 
+DVD_CONV_MAX_TAPS = 128
+
+
+class ConvDesc(ctypes.Structure):
+    """struct dvd_conv_desc (include/dvd_b200.h)."""
+    _fields_ = [('N', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int), ('Cin', ctypes.c_int),
+                ('OH', ctypes.c_int), ('OW', ctypes.c_int), ('Cout', ctypes.c_int), ('stride', ctypes.c_int),
+                ('ntaps', ctypes.c_int), ('kblock', ctypes.c_int), ('YH', ctypes.c_int), ('YW', ctypes.c_int),
+                ('oy_mul', ctypes.c_int), ('oy_add', ctypes.c_int), ('ox_mul', ctypes.c_int), ('ox_add', ctypes.c_int),
+                ('relu', ctypes.c_int), ('round_out', ctypes.c_int), ('bn_eps', ctypes.c_float),
+                ('dy', ctypes.c_byte * DVD_CONV_MAX_TAPS), ('dx', ctypes.c_byte * DVD_CONV_MAX_TAPS),
+                ('wt', ctypes.c_ubyte * DVD_CONV_MAX_TAPS)]
+
+
 class MlpCfg(ctypes.Structure):
     """struct dvd_mlp_cfg (include/dvd_b200.h)."""
     _fields_ = [('n_freq_xyz', ctypes.c_int), ('n_freq_t', ctypes.c_int), ('time_dependent', ctypes.c_int),
@@ -53,8 +67,22 @@ SIGNATURES = {
     'dvd_adam_flat': [_P, _P, _P, _P, ctypes.c_long, _F, _F, _F, _F, _I, _F, _P],
     'dvd_bn_act_fwd': [_P, _P, _P, _P, _P, _P, _F, _P, ctypes.c_long, _I, _I, _P],
     'dvd_bn_act_bwd': [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, ctypes.c_long, _I, _I, _P],
-    'dvd_upsample2x_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
-    'dvd_upsample2x_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'dvd_upsample2x_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'dvd_upsample2x_bwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    'dvd_conv2d_nhwc': [ctypes.POINTER(ConvDesc)] + [_P] * 11 + [_P],
+    'dvd_conv2d_pack': [_P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _I, _I, _I, _I, _I, _I, _P, _P, _F, _P],
+    'dvd_conv2d_wgrad': [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long,
+                         _I, _I, _P, _P, _P, _P],
+    'dvd_round_tf32': [_P, _P, ctypes.c_long, _P],
+    'dvd_relu_bwd_colsum': [_P, _P, _P, _P, _P, _P, _F, _P, ctypes.c_long, _I, _I, _P],
+    'dvd_maxpool3x3s2_fwd': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'dvd_maxpool3x3s2_bwd': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'dvd_stem_fwd': [_P, _P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _P, _P, _P, _F,
+                     ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _P, _I, _I, _I, _I, _P],
+    'dvd_stem_wgrad': [_P, _P, _P, _P, _P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _P, _P, _F, _P, _P,
+                       ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _P, _I, _I, _I, _P],
+    'dvd_head_fwd': [_P, _P, _P, _P, ctypes.c_long, _P],
+    'dvd_head_bwd': [_P, _P, _P, _P, _P, _P, _P, ctypes.c_long, _I, _I, _P],
     'dvd_conv_pack_weight': [_P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _I, _I, _I, _I, _P],
     'dvd_conv_nhwc_wgrad': [_P, _P, _P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _I, _I, _I, _I, _I, _I, _P],
     'dvd_conv_nhwc_fwd': [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

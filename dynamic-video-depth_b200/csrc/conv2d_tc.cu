@@ -1,0 +1,759 @@
+// Depth-net convolutions (every class of the MiDaS / ResNeXt101-32x8d stack) on the 5th-generation tensor cores.
+//
+// One implicit-GEMM kernel family on NHWC fp32 tensors whose values are already rounded to TF32 (round-to-nearest) by
+// the kernel that produced them ("rounded-operand contract"): tcgen05.mma.kind::tf32, SS mode, fp32
+// accumulators in tensor memory. Replaces cuDNN behind torch.nn.Conv2d / convolution_backward for
+//   dense 1x1 / 3x3 stride 1     third_party/midas_blocks.py:53-68,121-168; third_party/MiDaS.py:188-195; torchvision Bottleneck conv1/conv3
+//   1x1 / 3x3 stride 2           torchvision Bottleneck.downsample, conv2 of the first block of layer2-4
+//   grouped 3x3 (32 groups)      torchvision Bottleneck.conv2 (ResNeXt), as block-diagonal 64-channel GEMM blocks
+//   the data gradient of each    same kernel: transposed (BatchNorm-scaled) weight image, a tap table instead of a fixed
+//                                3x3 stencil, stride-2 gradients as 4 sub-pixel phases with a strided store
+//   the weight gradient of each  conv_wgrad_kernel below (K = pixels, both operands MN-major)
+// with the elementwise neighbours folded into the epilogue:  y = round_tf32(mask * relu(acc * scale + shift + res + res2))
+// (eval-mode BatchNorm / bias, residual adds, ReLU forward; residual-gradient add and ReLU mask backward).
+//
+//   D[128 pixels, NT channels] += sum over taps t, 32-channel chunks c of
+//     A_t,c [128 px x 32 ch]  TMA box {32 ch, TW, TH, 1} of the NHWC input at stride * tile origin + (dy_t, dx_t), element
+//                             stride = conv stride; out-of-image elements are zero-filled by the hardware (= padding);
+//                             lands as the canonical SWIZZLE_128B K-major image
+//   x W_t,c [NT x 32]         TMA box {32, NT, 1} of the packed weight image [tap][rows][cols]
+// One persistent CTA per SM: warp 0 = TMA producer (ring of kStages stages), warp 1 = MMA issuer and tensor-memory owner
+// (two accumulators: the epilogue of tile i overlaps the MMAs of tile i+1), warps 2-5 = epilogue: tcgen05.ld -> registers
+// -> swizzled shared-memory staging -> one TMA store per warp and 32-channel block (full 128-byte lines; ragged tiles are
+// clipped by the hardware).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace dvd {
+namespace {
+
+using namespace tc;
+
+constexpr int kStages = 4;
+constexpr int kThreads = 192;               // TMA producer, MMA issuer, 4 epilogue warps
+constexpr int kABytes = 128 * 128;          // 128 pixels x 32 fp32 channels
+constexpr int kMaxNT = 256;
+constexpr int kStageBytes = kABytes + kMaxNT * 128;
+constexpr int kStgBytes = 32 * 128;         // staging: 32 pixel rows x 32 channels
+constexpr int kOffStg = kStages * kStageBytes;              // 4 warps x 2 buffers
+constexpr int kOffAff = kOffStg + 8 * kStgBytes;            // scale[256] | shift[256]
+constexpr int kOffBar = kOffAff + 2 * kMaxNT * 4;
+constexpr size_t kSmem = kOffBar + 256;
+
+struct ConvParams {
+  dvd_conv_desc d;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* var;
+  const float* res;
+  const float* res2;
+  const float* mask;
+  float* y;
+  int TW, TH, tiles_w, tiles_h;   // pixel tile = TH x TW = 128 over the (OH, OW) grid
+  int NT;                         // output channels per tile
+  int kchunks;                    // 32-channel chunks per tap
+  int tma_store;                  // epilogue through shared memory + TMA store (identity output mapping, NT % 32 == 0)
+  int sbw, sbh;                   // per-warp store box: sbw x sbh = 32 pixels
+};
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs (fp32 words whose low 13 mantissa bits are zero), K = 8 per instruction
+__device__ __forceinline__ void umma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t o;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
+  return __uint_as_float(o);
+}
+
+struct Tile {
+  int n0, img, h0, w0;
+};
+__device__ __forceinline__ Tile decode_tile(const ConvParams& P, int tile, int m_tiles) {
+  Tile t;
+  const int nt = tile / m_tiles, m = tile - nt * m_tiles;
+  t.n0 = nt * P.NT;
+  const int per_img = P.tiles_w * P.tiles_h;
+  t.img = m / per_img;
+  const int r = m - t.img * per_img;
+  const int th = r / P.tiles_w;
+  t.h0 = th * P.TH;
+  t.w0 = (r - th * P.tiles_w) * P.TW;
+  return t;
+}
+
+// acc -> mask * relu(acc * scale + shift + res + res2), optionally rounded to TF32; NC consecutive channels of one pixel
+template <int NC>
+__device__ __forceinline__ void epilogue_math(const ConvParams& P, uint32_t (&r)[NC], const float* aff, const float* rrow,
+                                              const float* r2row, const float* mrow) {
+#pragma unroll
+  for (int j = 0; j < NC; j += 4) {
+    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    if (aff) {
+      const float4 sc = *reinterpret_cast<const float4*>(aff + j), sh = *reinterpret_cast<const float4*>(aff + kMaxNT + j);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+    }
+    if (rrow) {
+      const float4 a = *reinterpret_cast<const float4*>(rrow + j);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    if (r2row) {
+      const float4 a = *reinterpret_cast<const float4*>(r2row + j);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    if (P.d.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (mrow) {
+      const float4 m = *reinterpret_cast<const float4*>(mrow + j);
+      v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+    }
+    if (P.d.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    r[j] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y); r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                               const __grid_constant__ CUtensorMap mapW,
+                                                               const __grid_constant__ CUtensorMap mapY,
+                                                               const __grid_constant__ ConvParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + kStages;            // [kStages]
+  uint64_t* acc_full = bars + 2 * kStages;     // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* aff_mem = reinterpret_cast<float*>(smem + kOffAff);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("dvd_b200: conv2d_tc_kernel: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 512);
+  } else if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    if (P.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapY) : "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+
+  const int m_tiles = P.d.N * P.tiles_w * P.tiles_h;
+  const int n_tiles = P.d.Cout / P.NT;
+  const int ntiles = m_tiles * n_tiles;
+  const int ksteps = P.d.ntaps * P.kchunks;
+  const uint32_t stage_tx = (uint32_t)kABytes + (uint32_t)P.NT * 128u;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const Tile T = decode_tile(P, tile, m_tiles);
+        const int kbase = P.d.kblock ? (T.n0 / P.d.kblock) * P.d.kblock : 0;
+        const int ws = T.w0 * P.d.stride, hs = T.h0 * P.d.stride;
+        for (int t = 0; t < P.d.ntaps; ++t) {
+          const int dy = P.d.dy[t], dx = P.d.dx[t], wt = P.d.wt[t];
+          for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+            uint8_t* st = smem + (size_t)s * kStageBytes;
+            mbar_wait(&empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full[s], stage_tx);
+            tma_load_4d(st, &mapA, kbase + kc * 32, ws + dx, hs + dy, T.img, &full[s]);
+            tma_load_3d(st + kABytes, &mapW, kc * 32, T.n0, wt, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, P.NT);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], aph ^ 1u);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem + buf * (uint32_t)kMaxNT;
+        for (int k = 0; k < ksteps; ++k, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss_tf32(d, make_sdesc_k_sw128(sa + ks * 32), make_sdesc_k_sw128(sb + ks * 32), idesc, (k | ks) ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue: one pixel (accumulator row) per thread =====
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint8_t* stg = smem + kOffStg + (size_t)q * 2 * kStgBytes;
+    const bool has_aff = P.gamma != nullptr || P.bias != nullptr;
+    uint32_t lt = 0, nstore = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
+      const Tile T = decode_tile(P, tile, m_tiles);
+      const int h = T.h0 + row / P.TW, w = T.w0 + row % P.TW;
+      const int yh = h * P.d.oy_mul + P.d.oy_add, yw = w * P.d.ox_mul + P.d.ox_add;
+      const bool valid = h < P.d.OH && w < P.d.OW && yh < P.d.YH && yw < P.d.YW;
+      const size_t off = (((size_t)T.img * P.d.YH + yh) * P.d.YW + yw) * P.d.Cout + T.n0;
+      const float* rrow = (P.res && valid) ? P.res + off : nullptr;
+      const float* r2row = (P.res2 && valid) ? P.res2 + off : nullptr;
+      const float* mrow = (P.mask && valid) ? P.mask + off : nullptr;
+      float* yrow = P.y + off;
+      if (has_aff) {
+        // fold BatchNorm / bias of this tile's channels once: y = acc * scale + shift
+        asm volatile("bar.sync 2, 128;" ::: "memory");      // previous tile's readers are done
+        for (int i = row; i < P.NT; i += 128) {
+          const int c = T.n0 + i;
+          float sc = 1.f, sh = 0.f;
+          if (P.gamma) {
+            sc = __ldg(P.gamma + c) * rsqrtf(__ldg(P.var + c) + P.d.bn_eps);
+            sh = __ldg(P.beta + c) - __ldg(P.mean + c) * sc;
+          }
+          if (P.bias) sh = fmaf(__ldg(P.bias + c), sc, sh);
+          aff_mem[i] = sc;
+          aff_mem[kMaxNT + i] = sh;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+      mbar_wait(&acc_full[buf], aph);
+      tc_fence_after();
+      const uint32_t d = tmem + buf * (uint32_t)kMaxNT + lane_base;
+      if (P.tma_store) {
+        const int bh0 = T.h0 + (q * 32) / P.TW, bw0 = T.w0 + (q * 32) % P.TW;
+        for (int c0 = 0; c0 < P.NT; c0 += 32, ++nstore) {
+          uint32_t r[32];
+          tmem_ld32(d + c0, r);
+          tmem_ld_wait();
+          if (c0 + 32 >= P.NT) {                  // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+          }
+          epilogue_math<32>(P, r, has_aff ? aff_mem + c0 : nullptr, rrow ? rrow + c0 : nullptr, r2row ? r2row + c0 : nullptr,
+                            mrow ? mrow + c0 : nullptr);
+          uint8_t* sb = stg + (nstore & 1u) * kStgBytes;
+          if (lane == 0) bulk_wait_read<1>();      // the store that last read this buffer has drained it
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&mapY, sb, T.n0 + c0, bw0, bh0, T.img);
+            bulk_commit();
+          }
+        }
+      } else {
+        for (int c0 = 0; c0 < P.NT; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(d + c0, r);
+          tmem_ld_wait();
+          epilogue_math<16>(P, r, has_aff ? aff_mem + c0 : nullptr, rrow ? rrow + c0 : nullptr, r2row ? r2row + c0 : nullptr,
+                            mrow ? mrow + c0 : nullptr);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<uint4*>(yrow + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+      }
+    }
+    if (P.tma_store && lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight images. weight[co, ci_local, ky, kx] (arbitrary element strides), groups of `cpg` in-channels (cpg = Cin: dense).
+//   mode 0 (forward)        out[t][co][c]          c over Cin (dense) or over the `kblock` in-channels of co's block
+//   mode 1 (data gradient)  out[t][ci][c]          c over Cout (dense) or over the `kblock` out-channels of ci's block,
+//                                                  times the eval-BatchNorm scale gamma * rsqrt(var + eps) of that out-channel
+// t = ky * k + kx (never flipped: the tap table of the launch carries the offsets). Entries outside a channel's group are
+// zero (block-diagonal image of a grouped convolution). Values rounded to TF32 (RN).
+__global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict__ w, long s_co, long s_ci, long s_ky, long s_kx,
+                                                        float* __restrict__ out, int Cout, int Cin, int k, int cpg, int kblock,
+                                                        int mode, const float* __restrict__ gamma, const float* __restrict__ var,
+                                                        float eps) {
+  const int rows = mode ? Cin : Cout;
+  const int cols = kblock ? kblock : (mode ? Cout : Cin);
+  const long n = (long)k * k * rows * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const long q = i / cols;
+    const int r = (int)(q % rows), t = (int)(q / rows);
+    const int ky = t / k, kx = t - ky * k;
+    const int cabs = kblock ? (r / kblock) * kblock + c : c;     // absolute channel index of the column
+    const int co = mode ? cabs : r, ci = mode ? r : cabs;
+    float v = 0.f;
+    if (co / (Cout / (Cin / cpg)) == ci / cpg) {                 // same group (dense: one group)
+      v = w[co * s_co + (ci % cpg) * s_ci + ky * s_ky + kx * s_kx];
+      if (mode && gamma) v *= gamma[co] * rsqrtf(var[co] + eps);
+    }
+    out[i] = round_tf32(v);
+  }
+}
+
+// =====================================================================================================================
+// Weight gradient:  D[m][n] += sum over pixels  Mop[px (+off), m] * Nop[px (+off), n]
+// normally Mop = gy (out-channels), Nop = x shifted by the tap and sampled with the convolution stride; `swap` exchanges
+// the roles (needs 128 | M-channels). GEMM with K = pixels: both operands MN-major (channel contiguous). A 64-pixel TMA box
+// {32 ch, TW, TH, 1} lands as 64 rows of 128 bytes in the SWIZZLE_128B_BASE32B image (UMMA layout type 1); one MMA consumes
+// 8 pixels. Split-K over pixel tiles across CTAs; partial sums leave through fp32 reductions into the caller's gradient
+// buffer (any strides). Extras in the epilogue, all on the out-channel rows (swap = 0 only):
+//   * eval-BatchNorm scale: dW[co] = sc[co] * sum gm X  (gm = the un-scaled masked gradient the data gradient also consumes)
+//   * dgamma[co] += rstd[co] * <W[co], sum gm X>        (d/dgamma of BN(conv(x)) without touching any activation)
+//   * grouped convolutions: only the diagonal 128-channel blocks are computed and only in-group entries leave.
+constexpr int kWgStages = 2;
+constexpr int kWgPx = 64;                         // pixels (K) per stage
+constexpr int kWgBox = kWgPx * 128;               // bytes of one {32 ch, 64 px} box
+constexpr int kWgStageBytes = (4 + 8) * kWgBox;   // M: 128 channels, N: up to 256 channels
+constexpr size_t kWgSmem = (size_t)kWgStages * kWgStageBytes + 256;
+
+struct WgradParams {
+  float* dw;
+  const float* w;                  // parameter tensor (same strides as dw), only read for dgamma
+  long s_m, s_n, s_ky, s_kx;       // element strides of the M / N channel index and of the kernel taps
+  int N, OH, OW;                   // pixel grid of gy
+  int Mch, Nch;                    // channel counts of the two operands
+  int ntaps, ksize, stride, swap;
+  int TW, TH, tiles_w, tiles_h;    // 64-pixel tiles
+  int NT;                          // N channels per output tile
+  int ksplit;
+  int cpg;                         // > 0: grouped (diagonal blocks, NT = 128)
+  const float* gamma;              // eval BatchNorm of the out-channels (or null)
+  const float* var;
+  float eps;
+  float* dgamma;
+  signed char dy[DVD_CONV_MAX_TAPS], dx[DVD_CONV_MAX_TAPS];
+  unsigned char wt[DVD_CONV_MAX_TAPS];
+};
+
+__device__ __forceinline__ uint64_t make_sdesc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) { return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
+
+__global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapM,
+                                                          const __grid_constant__ CUtensorMap mapN,
+                                                          const __grid_constant__ WgradParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWgStages * kWgStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWgStages;
+  uint64_t* acc_full = bars + 2 * kWgStages;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("dvd_b200: conv_wgrad_kernel: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 256);
+  } else if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+
+  // this CTA: output tile (tap, 128 M-channels, NT N-channels) and a contiguous range of pixel tiles
+  const int out_tile = blockIdx.x / P.ksplit, part = blockIdx.x - out_tile * P.ksplit;
+  const int n_m = P.Mch / 128, n_n = P.cpg ? 1 : P.Nch / P.NT;
+  const int t = out_tile / (n_m * n_n);
+  const int rem = out_tile - t * (n_m * n_n);
+  const int m0 = (rem / n_n) * 128;
+  const int n0 = P.cpg ? m0 : (rem % n_n) * P.NT;
+  const int dy = P.dy[t], dx = P.dx[t];
+  const int px_tiles = P.N * P.tiles_h * P.tiles_w;
+  const int per = (px_tiles + P.ksplit - 1) / P.ksplit;
+  const int kt0 = part * per, kt1 = min(px_tiles, kt0 + per);
+  const int nb = P.NT / 32;
+  const uint32_t stage_tx = (uint32_t)(4 + nb) * kWgBox;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int kt = kt0; kt < kt1; ++kt, ++it) {
+        const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
+        const int img = kt / (P.tiles_h * P.tiles_w), r = kt - img * (P.tiles_h * P.tiles_w);
+        const int h0 = (r / P.tiles_w) * P.TH, w0 = (r % P.tiles_w) * P.TW;
+        // gy is sampled on the plain pixel grid, x at stride * pixel + tap offset
+        const int gw = w0, gh = h0, xw = w0 * P.stride + dx, xh = h0 * P.stride + dy;
+        const int mw = P.swap ? xw : gw, mh = P.swap ? xh : gh, nw = P.swap ? gw : xw, nh = P.swap ? gh : xh;
+        uint8_t* st = smem + (size_t)s * kWgStageBytes;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], stage_tx);
+        for (int j = 0; j < 4; ++j) tma_load_4d(st + j * kWgBox, &mapM, m0 + 32 * j, mw, mh, img, &full[s]);
+        for (int j = 0; j < nb; ++j) tma_load_4d(st + (4 + j) * kWgBox, &mapN, n0 + 32 * j, nw, nh, img, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_mn(128, P.NT);
+      uint32_t it = 0;
+      for (int kt = kt0; kt < kt1; ++kt, ++it) {
+        const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * kWgStageBytes), sb = sa + 4 * kWgBox;
+#pragma unroll
+        for (int ks = 0; ks < kWgPx / 8; ++ks)
+          umma_ss_tf32(tmem, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox), make_sdesc_mn_sw128_32b(sb + ks * 1024, kWgBox), idesc,
+                       (it | ks) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (kt1 > kt0) {
+    // epilogue: accumulator row = M channel, columns = N channels of this tile
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const uint32_t d = tmem + ((uint32_t)(q * 32) << 16);
+    const int wt = P.wt[t];
+    const long tap_off = (long)(wt / P.ksize) * P.s_ky + (long)(wt % P.ksize) * P.s_kx;
+    float* dst = P.dw + (long)m * P.s_m + tap_off;
+    const float* wrow = P.w ? P.w + (long)m * P.s_m + tap_off : nullptr;
+    float sc = 1.f, rstd = 0.f;
+    if (P.gamma) {
+      rstd = rsqrtf(__ldg(P.var + m) + P.eps);
+      sc = __ldg(P.gamma + m) * rstd;
+    }
+    float dot = 0.f;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    if (P.cpg) {
+      // diagonal block: columns of this row's group only; the warp's 32 rows cover max(cpg, 32) columns
+      const int win = P.cpg > 32 ? P.cpg : 32;
+      const int wstart = ((q * 32) / win) * win;
+      const int g_row = (q * 32 + lane) / P.cpg;
+      for (int c0 = wstart; c0 < wstart + win; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(d + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = c0 + j;
+          if (col / P.cpg == g_row) {
+            const float v = __uint_as_float(r[j]);
+            const long o = (long)(col % P.cpg) * P.s_n;
+            if (wrow) dot = fmaf(v, __ldg(wrow + o), dot);
+            atomicAdd(dst + o, v * sc);
+          }
+        }
+      }
+    } else {
+      for (int c0 = 0; c0 < P.NT; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(d + c0, r);
+        tmem_ld_wait();
+        if (wrow) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dot = fmaf(__uint_as_float(r[j]), __ldg(wrow + (long)(n0 + c0 + j) * P.s_n), dot);
+        }
+        if (P.s_n == 1 && ((reinterpret_cast<uintptr_t>(dst + n0 + c0) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + n0 + c0 + j), "f"(__uint_as_float(r[j]) * sc),
+                         "f"(__uint_as_float(r[j + 1]) * sc), "f"(__uint_as_float(r[j + 2]) * sc), "f"(__uint_as_float(r[j + 3]) * sc)
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + (long)(n0 + c0 + j) * P.s_n, __uint_as_float(r[j]) * sc);
+        }
+      }
+    }
+    if (P.dgamma) atomicAdd(P.dgamma + m, dot * rstd);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box, const cuuint32_t* elem_strides, CUtensorMapSwizzle swizzle) {
+  auto fn = encode_fn();
+  DVD_ARG_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                  elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DVD_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+// 4-D map of an NHWC tensor [N][H][W][C]; a box of {32 ch, bw, bh, 1} ELEMENTS sampled every `es` pixels
+int make_nhwc_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bw, int bh, int es, CUtensorMapSwizzle swizzle) {
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  const cuuint32_t box[4] = {32, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), 1};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  DVD_ARG_CHECK(bw * es <= 256 && bh * es <= 256, "TMA box too large (%d x %d at element stride %d)", bw, bh, es);
+  return make_map(m, ptr, 4, dims, strides, box, estr, swizzle);
+}
+
+// TH x TW = npx (power of two) tile over an H x W grid with the least padding
+void pick_tile(int H, int W, int npx, int max_tw, int* TW, int* TH) {
+  long best = -1;
+  for (int tw = npx < max_tw ? npx : max_tw; tw >= 8; tw >>= 1) {
+    const int th = npx / tw;
+    const long padded = (long)((W + tw - 1) / tw * tw) * ((H + th - 1) / th * th);
+    if (best < 0 || padded < best) { best = padded; *TW = tw; *TH = th; }
+  }
+}
+
+int per_device_attr(const void* func, size_t smem_bytes, bool (&done)[16]) {
+  int dev = 0;
+  DVD_CUDA_CALL(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) dev = 0;
+  if (!done[dev]) {
+    DVD_CUDA_CALL(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    done[dev] = true;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace dvd
+
+using namespace dvd;
+
+extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const float* w_img, const float* bias, const float* bn_gamma,
+                               const float* bn_beta, const float* bn_mean, const float* bn_var, const float* res, const float* res2,
+                               const float* mask, float* y, void* stream) {
+  DVD_ARG_CHECK(desc && x && w_img && y, "null pointer");
+  ConvParams P{};
+  P.d = *desc;
+  dvd_conv_desc& d = P.d;
+  DVD_ARG_CHECK(d.N >= 1 && d.H >= 1 && d.W >= 1 && d.OH >= 1 && d.OW >= 1, "bad shape N=%d H=%d W=%d OH=%d OW=%d", d.N, d.H, d.W, d.OH, d.OW);
+  DVD_ARG_CHECK(d.stride == 1 || d.stride == 2, "stride must be 1 or 2");
+  DVD_ARG_CHECK(d.ntaps >= 1 && d.ntaps <= DVD_CONV_MAX_TAPS, "ntaps out of range");
+  DVD_ARG_CHECK(d.kblock == 0 || (d.kblock % 32 == 0 && d.kblock <= kMaxNT && d.Cout % d.kblock == 0 && d.Cin % d.kblock == 0),
+                "bad kblock %d (Cin=%d Cout=%d)", d.kblock, d.Cin, d.Cout);
+  if (d.Cin % 32 != 0 || d.Cout % 16 != 0) {
+    set_error("dvd_conv2d_nhwc: needs Cin %% 32 == 0 and Cout %% 16 == 0 (Cin=%d Cout=%d)", d.Cin, d.Cout);
+    return -2;
+  }
+  DVD_ARG_CHECK(aligned16(x) && aligned16(w_img) && aligned16(y) && (!res || aligned16(res)) && (!res2 || aligned16(res2)) &&
+                    (!mask || aligned16(mask)),
+                "tensors must be 16-byte aligned");
+  DVD_ARG_CHECK((bn_gamma != nullptr) == (bn_beta != nullptr) && (bn_gamma != nullptr) == (bn_mean != nullptr) &&
+                    (bn_gamma != nullptr) == (bn_var != nullptr),
+                "BatchNorm needs all of gamma, beta, mean, var (or none)");
+  P.bias = bias; P.gamma = bn_gamma; P.beta = bn_beta; P.mean = bn_mean; P.var = bn_var;
+  P.res = res; P.res2 = res2; P.mask = mask; P.y = y;
+  P.NT = d.kblock ? d.kblock : (d.Cout >= kMaxNT ? kMaxNT : d.Cout);
+  if (d.Cout % P.NT != 0) { set_error("dvd_conv2d_nhwc: Cout=%d is not a multiple of the %d-channel tile", d.Cout, P.NT); return -2; }
+  P.kchunks = (d.kblock ? d.kblock : d.Cin) / 32;
+  const bool identity_out = d.oy_mul == 1 && d.ox_mul == 1 && d.oy_add == 0 && d.ox_add == 0 && d.YH == d.OH && d.YW == d.OW;
+  const bool pointwise = d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && d.stride == 1 && identity_out && d.H == d.OH && d.W == d.OW;
+  int inN = d.N, inH = d.H, inW = d.W;
+  if (pointwise) {
+    // a 1x1 stride-1 convolution is a plain GEMM over all N*H*W pixels: one "image" of P x 1
+    const long Pn = (long)d.N * d.H * d.W;
+    DVD_ARG_CHECK(Pn < (1L << 31), "too many pixels");
+    inN = 1; inH = 1; inW = (int)Pn;
+    d.N = 1; d.OH = 1; d.OW = (int)Pn; d.YH = 1; d.YW = (int)Pn;
+    P.TW = 128; P.TH = 1;
+  } else {
+    pick_tile(d.OH, d.OW, 128, 128, &P.TW, &P.TH);   // the TMA box spans TW * stride <= 256 input pixels
+  }
+  P.tiles_w = (d.OW + P.TW - 1) / P.TW;
+  P.tiles_h = (d.OH + P.TH - 1) / P.TH;
+  P.tma_store = identity_out && (P.NT % 32 == 0);
+  P.sbw = P.TW < 32 ? P.TW : 32;
+  P.sbh = 32 / P.sbw;
+  CUtensorMap mapA, mapW, mapY;
+  if (int e = make_nhwc_map(&mapA, x, inN, inH, inW, d.Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  {
+    int max_wt = 0;
+    for (int t = 0; t < d.ntaps; ++t) max_wt = d.wt[t] > max_wt ? d.wt[t] : max_wt;
+    const int Kw = d.kblock ? d.kblock : d.Cin;
+    const cuuint64_t dims[3] = {(cuuint64_t)Kw, (cuuint64_t)d.Cout, (cuuint64_t)(max_wt + 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)Kw * 4, (cuuint64_t)d.Cout * Kw * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)P.NT, 1};
+    const cuuint32_t ones[3] = {1, 1, 1};
+    if (int e = make_map(&mapW, w_img, 3, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  }
+  if (P.tma_store) {
+    if (int e = make_nhwc_map(&mapY, y, d.N, d.YH, d.YW, d.Cout, P.sbw, P.sbh, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  } else {
+    mapY = mapA;
+  }
+  static bool attr_done[16] = {};
+  if (int e = per_device_attr((const void*)conv2d_tc_kernel, kSmem, attr_done)) return e;
+  const long ntiles = (long)d.N * P.tiles_w * P.tiles_h * (d.Cout / P.NT);
+  int grid = num_sms();
+  if (ntiles < grid) grid = (int)ntiles;
+  conv2d_tc_kernel<<<grid, kThreads, kSmem, (cudaStream_t)stream>>>(mapA, mapW, mapY, P);
+  DVD_CUDA_LAUNCH_CHECK("conv2d_tc_kernel");
+  return 0;
+}
+
+extern "C" int dvd_conv2d_pack(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx, float* w_img,
+                               int Cout, int Cin, int ksize, int groups, int kblock, int mode, const float* bn_gamma,
+                               const float* bn_var, float bn_eps, void* stream) {
+  DVD_ARG_CHECK(weight && w_img, "null pointer");
+  DVD_ARG_CHECK(Cout >= 1 && Cin >= 1 && ksize >= 1 && ksize <= 11 && groups >= 1 && Cin % groups == 0 && Cout % groups == 0,
+                "bad weight shape");
+  DVD_ARG_CHECK((groups == 1) == (kblock == 0), "kblock must be set exactly for grouped convolutions");
+  const int cpg = Cin / groups;
+  if (kblock) DVD_ARG_CHECK(Cin == Cout && kblock % cpg == 0 && Cin % kblock == 0, "grouped: needs Cin == Cout and cpg | kblock | Cin");
+  DVD_ARG_CHECK((bn_gamma != nullptr) == (bn_var != nullptr), "BatchNorm scale needs gamma and var");
+  const int rows = mode ? Cin : Cout, cols = kblock ? kblock : (mode ? Cout : Cin);
+  const long n = (long)ksize * ksize * rows * cols;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+  conv_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(weight, stride_co, stride_ci, stride_ky, stride_kx, w_img, Cout, Cin, ksize,
+                                                           cpg, kblock, mode, bn_gamma, bn_var, bn_eps);
+  DVD_CUDA_LAUNCH_CHECK("conv_pack_kernel");
+  return 0;
+}
+
+extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const float* gy, float* dweight, const float* weight,
+                                long stride_co, long stride_ci, long stride_ky, long stride_kx, int ksize, int groups,
+                                const float* bn_gamma, const float* bn_var, float* dgamma, void* stream) {
+  DVD_ARG_CHECK(desc && x && gy && dweight, "null pointer");
+  const dvd_conv_desc& d = *desc;
+  DVD_ARG_CHECK(d.N >= 1 && d.H >= 1 && d.W >= 1 && d.OH >= 1 && d.OW >= 1, "bad shape");
+  DVD_ARG_CHECK(d.stride == 1 || d.stride == 2, "stride must be 1 or 2");
+  DVD_ARG_CHECK(d.ntaps >= 1 && d.ntaps <= DVD_CONV_MAX_TAPS, "ntaps out of range");
+  DVD_ARG_CHECK(aligned16(x) && aligned16(gy), "tensors must be 16-byte aligned");
+  DVD_ARG_CHECK((bn_gamma != nullptr) == (bn_var != nullptr) && (!dgamma || (bn_gamma && weight)), "BatchNorm extras need gamma, var (and weight for dgamma)");
+  WgradParams P{};
+  P.dw = dweight; P.w = dgamma ? weight : nullptr;
+  P.N = d.N; P.OH = d.OH; P.OW = d.OW; P.ntaps = d.ntaps; P.ksize = ksize; P.stride = d.stride;
+  P.gamma = bn_gamma; P.var = bn_var; P.eps = d.bn_eps; P.dgamma = dgamma;
+  for (int t = 0; t < d.ntaps; ++t) { P.dy[t] = d.dy[t]; P.dx[t] = d.dx[t]; P.wt[t] = d.wt[t]; }
+  const int Cin = d.Cin, Cout = d.Cout;
+  if (groups > 1) {
+    P.cpg = Cin / groups;
+    if (Cin != Cout || Cin % 128 != 0 || 128 % P.cpg != 0) {
+      set_error("dvd_conv2d_wgrad: grouped needs Cin == Cout, 128 | C and cpg | 128 (C=%d groups=%d)", Cin, groups);
+      return -2;
+    }
+    P.swap = 0; P.Mch = Cout; P.Nch = Cin; P.NT = 128;
+    P.s_m = stride_co; P.s_n = stride_ci;
+  } else if (Cout % 128 == 0 && Cin % 32 == 0 && (Cin <= 256 || Cin % 256 == 0)) {
+    P.swap = 0; P.Mch = Cout; P.Nch = Cin; P.NT = Cin >= 256 ? 256 : Cin;
+    P.s_m = stride_co; P.s_n = stride_ci;
+  } else if (Cin % 128 == 0 && Cout % 32 == 0 && (Cout <= 256 || Cout % 256 == 0) && !bn_gamma) {
+    P.swap = 1; P.Mch = Cin; P.Nch = Cout; P.NT = Cout >= 256 ? 256 : Cout;
+    P.s_m = stride_ci; P.s_n = stride_co;
+  } else {
+    set_error("dvd_conv2d_wgrad: unsupported channel counts Cin=%d Cout=%d", Cin, Cout);
+    return -2;
+  }
+  P.s_ky = stride_ky; P.s_kx = stride_kx;
+  int N = d.N, OH = d.OH, OW = d.OW, H = d.H, W = d.W;
+  const bool pointwise = d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && d.stride == 1 && d.H == d.OH && d.W == d.OW;
+  if (pointwise) {
+    const long Pn = (long)N * OH * OW;
+    DVD_ARG_CHECK(Pn < (1L << 31), "too many pixels");
+    N = 1; OH = 1; OW = (int)Pn; H = 1; W = (int)Pn;
+    P.N = 1; P.OH = 1; P.OW = (int)Pn;
+    P.TW = kWgPx; P.TH = 1;
+  } else {
+    pick_tile(OH, OW, kWgPx, kWgPx, &P.TW, &P.TH);
+  }
+  P.tiles_w = (OW + P.TW - 1) / P.TW;
+  P.tiles_h = (OH + P.TH - 1) / P.TH;
+  const int out_tiles = d.ntaps * (P.Mch / 128) * (P.cpg ? 1 : P.Nch / P.NT);
+  const int px_tiles = N * P.tiles_h * P.tiles_w;
+  int ksplit = (num_sms() + out_tiles - 1) / out_tiles;
+  if (ksplit > px_tiles) ksplit = px_tiles;
+  if (ksplit < 1) ksplit = 1;
+  P.ksplit = ksplit;
+  CUtensorMap mapG, mapX;
+  if (int e = make_nhwc_map(&mapG, gy, N, OH, OW, Cout, P.TW, P.TH, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  if (int e = make_nhwc_map(&mapX, x, N, H, W, Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
+  static bool attr_done[16] = {};
+  if (int e = per_device_attr((const void*)conv_wgrad_kernel, kWgSmem, attr_done)) return e;
+  if (P.swap)
+    conv_wgrad_kernel<<<out_tiles * ksplit, 192, kWgSmem, (cudaStream_t)stream>>>(mapX, mapG, P);
+  else
+    conv_wgrad_kernel<<<out_tiles * ksplit, 192, kWgSmem, (cudaStream_t)stream>>>(mapG, mapX, P);
+  DVD_CUDA_LAUNCH_CHECK("conv_wgrad_kernel");
+  return 0;
+}

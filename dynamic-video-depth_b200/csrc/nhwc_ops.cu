@@ -14,6 +14,15 @@ namespace dvd {
 
 constexpr int kElemThreads = 256;
 
+__device__ __forceinline__ float4 round4_tf32(float4 v) {
+  uint32_t a, b, c, d;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(a) : "f"(v.x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.y));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(c) : "f"(v.z));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(d) : "f"(v.w));
+  return make_float4(__uint_as_float(a), __uint_as_float(b), __uint_as_float(c), __uint_as_float(d));
+}
+
 // y = x * scale[c] + shift[c] (+ res) ; optional ReLU.   scale = gamma * rsqrt(var + eps), shift = beta - mean * scale
 __global__ void __launch_bounds__(kElemThreads) bn_act_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -104,7 +113,8 @@ __device__ __forceinline__ float src_index(int dst, float scale, bool align) {
 }
 
 __global__ void __launch_bounds__(kElemThreads) upsample2x_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N,
-                                                                      int H, int W, int c4, float sh, float sw, int align) {
+                                                                      int H, int W, int c4, float sh, float sw, int align,
+                                                                      int round_out) {
   const int OH = 2 * H, OW = 2 * W;
   const long total = (long)N * OH * OW * c4;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -126,13 +136,15 @@ __global__ void __launch_bounds__(kElemThreads) upsample2x_fwd_kernel(const floa
     o.y = hy * (hx * a00.y + lx * a01.y) + ly * (hx * a10.y + lx * a11.y);
     o.z = hy * (hx * a00.z + lx * a01.z) + ly * (hx * a10.z + lx * a11.z);
     o.w = hy * (hx * a00.w + lx * a01.w) + ly * (hx * a10.w + lx * a11.w);
+    if (round_out) o = round4_tf32(o);
     st_stream4(reinterpret_cast<float*>(y + i), o);
   }
 }
 
 // gather backward: input pixel (iy, ix) collects from every output pixel whose taps include it
 __global__ void __launch_bounds__(kElemThreads) upsample2x_bwd_kernel(const float4* __restrict__ g, float4* __restrict__ gx, int N,
-                                                                      int H, int W, int c4, float sh, float sw, int align) {
+                                                                      int H, int W, int c4, float sh, float sw, int align,
+                                                                      int round_out) {
   const int OH = 2 * H, OW = 2 * W;
   const long total = (long)N * H * W * c4;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(kElemThreads) upsample2x_bwd_kernel(const floa
         acc.z = fmaf(w, gv.z, acc.z); acc.w = fmaf(w, gv.w, acc.w);
       }
     }
-    gx[i] = acc;
+    gx[i] = round_out ? round4_tf32(acc) : acc;
   }
 }
 
@@ -221,24 +233,24 @@ extern "C" int dvd_bn_act_bwd(const float* g, const float* x, const float* y, co
   return 0;
 }
 
-extern "C" int dvd_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, int align_corners, void* stream) {
+extern "C" int dvd_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, int align_corners, int round_out, void* stream) {
   DVD_ARG_CHECK(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad arguments (C must be a multiple of 4)");
   const float sh = align_corners ? (H > 1 ? (float)(H - 1) / (2 * H - 1) : 0.f) : 0.5f;
   const float sw = align_corners ? (W > 1 ? (float)(W - 1) / (2 * W - 1) : 0.f) : 0.5f;
   const long total = (long)N * 4 * H * W * (C / 4);
   upsample2x_fwd_kernel<<<blocks_for(total), kElemThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4, sh,
-                                                                                    sw, align_corners);
+                                                                                    sw, align_corners, round_out);
   DVD_CUDA_LAUNCH_CHECK("upsample2x_fwd");
   return 0;
 }
 
-extern "C" int dvd_upsample2x_bwd(const float* g, float* gx, int N, int H, int W, int C, int align_corners, void* stream) {
+extern "C" int dvd_upsample2x_bwd(const float* g, float* gx, int N, int H, int W, int C, int align_corners, int round_out, void* stream) {
   DVD_ARG_CHECK(g && gx && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad arguments (C must be a multiple of 4)");
   const float sh = align_corners ? (H > 1 ? (float)(H - 1) / (2 * H - 1) : 0.f) : 0.5f;
   const float sw = align_corners ? (W > 1 ? (float)(W - 1) / (2 * W - 1) : 0.f) : 0.5f;
   const long total = (long)N * H * W * (C / 4);
   upsample2x_bwd_kernel<<<blocks_for(total), kElemThreads, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)gx, N, H, W, C / 4, sh,
-                                                                                    sw, align_corners);
+                                                                                    sw, align_corners, round_out);
   DVD_CUDA_LAUNCH_CHECK("upsample2x_bwd");
   return 0;
 }

@@ -560,7 +560,7 @@ class Upsample2x(torch.autograd.Function):
         y = torch.empty((N, C, 2 * H, 2 * W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         lib = _lib.load()
         LAUNCHES['n'] += 1
-        _lib.check(lib.dvd_upsample2x_fwd(_ptr(x), _ptr(y), N, H, W, C, int(align_corners), _stream()), 'dvd_upsample2x_fwd')
+        _lib.check(lib.dvd_upsample2x_fwd(_ptr(x), _ptr(y), N, H, W, C, int(align_corners), 0, _stream()), 'dvd_upsample2x_fwd')
         ctx.shape, ctx.align = (N, C, H, W), bool(align_corners)
         return y
 
@@ -571,7 +571,7 @@ class Upsample2x(torch.autograd.Function):
         gx = torch.empty((N, C, H, W), dtype=g.dtype, device=g.device, memory_format=torch.channels_last)
         lib = _lib.load()
         LAUNCHES['n'] += 1
-        _lib.check(lib.dvd_upsample2x_bwd(_ptr(g), _ptr(gx), N, H, W, C, int(ctx.align), _stream()), 'dvd_upsample2x_bwd')
+        _lib.check(lib.dvd_upsample2x_bwd(_ptr(g), _ptr(gx), N, H, W, C, int(ctx.align), 0, _stream()), 'dvd_upsample2x_bwd')
         return gx, None
 
 

@@ -186,8 +186,9 @@ int dvd_bn_act_bwd(const float* g, const float* x, const float* y, const float* 
                    long P, int C, int relu, void* stream);
 /* x2 bilinear up-sampling (third_party/midas_blocks.py:95-97 align_corners=False; :164-166 align_corners=True;
  * hourglass UpsamplingBilinear2d = True), NHWC [N,H,W,C] -> [N,2H,2W,C], and its adjoint.                      */
-int dvd_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, int align_corners, void* stream);
-int dvd_upsample2x_bwd(const float* g, float* gx, int N, int H, int W, int C, int align_corners, void* stream);
+int dvd_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, int align_corners, int round_out, void* stream);
+int dvd_upsample2x_bwd(const float* g, float* gx, int N, int H, int W, int C, int align_corners, int round_out, void* stream);
+/* round_out = 1: results stored rounded to TF32 (round-to-nearest) - they feed a tensor-core convolution (see below) */
 
 /* D1 / D2 dense stride-1 convolutions (1x1, 3x3 "same") on tcgen05 tensor cores, NHWC fp32 tensors, TF32 operands, fp32
  * accumulation:  y = act(BN(conv(x, w) + bias) + res)   - replaces torch.nn.Conv2d (cuDNN) followed by eval-mode
@@ -213,6 +214,84 @@ int dvd_conv_pack_weight(const float* weight, long stride_co, long stride_ci, lo
  * Cin % 32 == 0 (Cin <= 256 or a multiple of 256): returns -2 otherwise. Replaces cuDNN's convolution_backward weight path.  */
 int dvd_conv_nhwc_wgrad(const float* x, const float* gy, float* dweight, long stride_co, long stride_ci, long stride_ky,
                         long stride_kx, int N, int H, int W, int Cin, int Cout, int ksize, void* stream);
+
+
+/* ---- D1 / D1' depth-net convolutions, general form (csrc/conv2d_tc.cu) -------------------------------------------------
+ * One implicit-GEMM tcgen05 (TF32) kernel family for every convolution class of MiDaS / ResNeXt101-32x8d
+ * (third_party/MiDaS.py:188-246, third_party/midas_blocks.py:48-68,102-168, torchvision Bottleneck): dense and grouped,
+ * stride 1 and 2, forward and data gradient (tap table + sub-pixel phases), plus the weight gradient.
+ * ROUNDED-OPERAND CONTRACT: x (and gy) must hold values already rounded to TF32 with round-to-nearest - every kernel of this
+ * library that produces an activation or a gradient offers a `round` switch, and dvd_round_tf32 does it for foreign tensors -
+ * because the tensor core itself truncates the low 13 mantissa bits (a -7e-4 bias per layer otherwise).                    */
+#define DVD_CONV_MAX_TAPS 128
+typedef struct dvd_conv_desc {
+  int N, H, W, Cin;            /* input tensor x [N,H,W,Cin] (NHWC)                                                    */
+  int OH, OW, Cout;            /* output grid of THIS launch (tile space) and output channels                          */
+  int stride;                  /* 1 | 2: tap t of output pixel (oh,ow) reads x[stride*oh + dy[t], stride*ow + dx[t]] (zero outside) */
+  int ntaps;
+  int kblock;                  /* 0: dense (all Cin per output channel); else block-diagonal (grouped) with this block size */
+  int YH, YW;                  /* spatial size of the tensors y / res / res2 / mask                                    */
+  int oy_mul, oy_add, ox_mul, ox_add;   /* output pixel (oh,ow) is stored at y[oh*oy_mul+oy_add, ow*ox_mul+ox_add]     */
+  int relu;                    /* ReLU after the residual adds                                                         */
+  int round_out;               /* store TF32-rounded values (the output feeds another convolution)                     */
+  float bn_eps;
+  signed char dy[DVD_CONV_MAX_TAPS], dx[DVD_CONV_MAX_TAPS];
+  unsigned char wt[DVD_CONV_MAX_TAPS];  /* index of the tap's [rows][cols] slice in the packed weight image            */
+} dvd_conv_desc;
+
+/* y = round( [mask > 0] * relu( conv(x, w_img) * scale + shift + res + res2 ) )
+ * scale/shift fold the conv bias and / or an eval-mode BatchNorm (gamma, beta, mean, var: all four or none); res, res2, mask
+ * are NHWC tensors shaped like y, each may be NULL. Needs Cin % 32 == 0, Cout % 16 == 0 (Cout <= 256 or 256 | Cout).      */
+int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const float* w_img, const float* bias, const float* bn_gamma,
+                    const float* bn_beta, const float* bn_mean, const float* bn_var, const float* res, const float* res2,
+                    const float* mask, float* y, void* stream);
+
+/* weight[co, ci_local, ky, kx] (element strides given; groups of Cin/groups in-channels) -> TF32-rounded image
+ *   mode 0: forward        [k*k][Cout][Cin or kblock]
+ *   mode 1: data gradient  [k*k][Cin][Cout or kblock], multiplied by gamma*rsqrt(var+eps) of the out-channel when given
+ * grouped convolutions (groups > 1) are packed block-diagonally with `kblock` channels per block (kblock = 0 when dense).   */
+int dvd_conv2d_pack(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx, float* w_img,
+                    int Cout, int Cin, int ksize, int groups, int kblock, int mode, const float* bn_gamma,
+                    const float* bn_var, float bn_eps, void* stream);
+
+/* dweight[co, ci_local, ky, kx] += sc[co] * sum_px gy[px, co] * x[stride*px + (dy,dx)(tap), ci]   (fp32 reductions, any strides)
+ * for the taps of `desc` (wt[t] = ky*ksize + kx). With an eval-mode BatchNorm behind the convolution, gy is the UN-scaled
+ * masked gradient, sc = gamma*rsqrt(var+eps), and dgamma[co] += rsqrt(var+eps) * <weight[co], sum gy x> (weight = the
+ * parameter tensor, same strides as dweight). Needs (128 | Cout and 32 | Cin) or (128 | Cin and 32 | Cout, no BatchNorm);
+ * grouped: Cin == Cout, 128 | C.                                                                                              */
+int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const float* gy, float* dweight, const float* weight,
+                     long stride_co, long stride_ci, long stride_ky, long stride_kx, int ksize, int groups,
+                     const float* bn_gamma, const float* bn_var, float* dgamma, void* stream);
+
+/* ---- CUDA-core members of the MiDaS path (csrc/depth_ops.cu), NHWC fp32 -------------------------------------------------- */
+/* y = round-to-nearest TF32 of x (n % 4 == 0): entry of foreign tensors into the rounded-operand contract                   */
+int dvd_round_tf32(const float* x, float* y, long n, void* stream);
+/* gm = g * [y > 0] (y NULL: gm = g), optionally TF32-rounded and optionally stored (gm NULL: sums only);
+ * colsum[c] += sum_p gm[p,c] (bias / BatchNorm-beta gradient); dgamma[c] -= mean[c]*rsqrt(var[c]+eps)*sum_p gm[p,c]          */
+int dvd_relu_bwd_colsum(const float* g, const float* y, float* gm, float* colsum, const float* bn_mean, const float* bn_var,
+                        float bn_eps, float* dgamma, long P, int C, int round_out, void* stream);
+/* torchvision ResNet.maxpool = MaxPool2d(3, stride 2, padding 1): x [N,H,W,C] -> y [N,OH,OW,C], idx = window position of the
+ * (first) maximum; backward gathers g through idx into gx [N,H,W,C] (overwrites).                                            */
+int dvd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int N, int H, int W, int C, void* stream);
+int dvd_maxpool3x3s2_bwd(const float* g, const unsigned char* idx, float* gx, int N, int H, int W, int C, void* stream);
+/* ResNeXt stem on the raw image: y = relu(bn1(conv1((x - mean)/std)))  (third_party/MiDaS.py:213-218; torchvision ResNet.conv1
+ * 7x7 stride 2 pad 3, 3 -> 64). x_nchw [N,3,H,W]; weight [64,3,7,7] with the given element strides; norm_mean3 / norm_std3 are
+ * HOST pointers to 3 floats (NULL: no normalisation); y [N,OH,OW,64] NHWC.                                                    */
+int dvd_stem_fwd(const float* x_nchw, const float* weight, long s_co, long s_ci, long s_ky, long s_kx, const float* bn_gamma,
+                 const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps, const float* norm_mean3,
+                 const float* norm_std3, float* y, int N, int H, int W, int round_out, void* stream);
+/* its parameter gradients from g = dL/dy (the ReLU mask is taken from a0 = y): dweight / dgamma / dbeta are ACCUMULATED;
+ * scratch: 147*64 + 64 floats (zeroed by the call).                                                                           */
+int dvd_stem_wgrad(const float* x_nchw, const float* g, const float* a0, const float* weight, float* dweight, long s_co,
+                   long s_ci, long s_ky, long s_kx, const float* bn_gamma, const float* bn_mean, const float* bn_var,
+                   float bn_eps, float* dgamma, float* dbeta, const float* norm_mean3, const float* norm_std3, float* scratch,
+                   int N, int H, int W, void* stream);
+/* head: depth[p] = 10000 / max(relu(<x[p,0:32], w> + b), 1e-2)  (scratch.output_conv[4..5] + MiDaS.py:240-242); backward
+ * from g_depth: gx [P,32] overwritten (relu_mask = 1: times [x > 0], i.e. w.r.t. the pre-activation of the ReLU that produced x;
+ * optionally TF32-rounded), gw[32] and gb[1] ACCUMULATED.                                                                     */
+int dvd_head_fwd(const float* x, const float* w, const float* b, float* depth, long P, void* stream);
+int dvd_head_bwd(const float* x, const float* w, const float* b, const float* g_depth, float* gx, float* gw, float* gb, long P,
+                 int relu_mask, int round_out, void* stream);
 
 #ifdef __cplusplus
 }

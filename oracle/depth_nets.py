@@ -57,8 +57,8 @@ def _fusion(sd, pre, a, b=None):
 
 def midas_forward(sd, x, normalize_input=True, resize=None):
     if normalize_input:
-        mean = torch.tensor([0.485, 0.456, 0.406], dtype=x.dtype).view(1, 3, 1, 1)
-        std = torch.tensor([0.229, 0.224, 0.225], dtype=x.dtype).view(1, 3, 1, 1)
+        mean = torch.tensor([0.485, 0.456, 0.406], dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225], dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
         x = (x - mean) / std
     orig = x.shape[-2:]
     if resize is not None:

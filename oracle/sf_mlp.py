@@ -21,7 +21,7 @@ def freqs(n_freq, dtype=torch.float32):
 
 def periodic_embed(x, n_freq):
     """x [B,C,H,W] → [B, C·(1+2·n_freq), H, W]: [x, cos(f_k x) for k, sin(f_k x) for k]."""
-    f = freqs(n_freq, x.dtype)
+    f = freqs(n_freq, x.dtype).to(x.device)
     out = [x]
     for fn in (torch.cos, torch.sin):
         for k in range(n_freq):

@@ -1,0 +1,71 @@
+"""MiDaS on the repo's own kernels (dvd_b200.depth_engine: explicit forward / backward schedule over the tcgen05 convolutions)
+against the CPU oracle (oracle/depth_nets.py, torch fp32 + autograd): depth maps within 1e-3 (TF32 convolutions), parameter
+gradients by max-norm and by share of elements within tolerance."""
+import pytest
+import torch
+
+from conftest import rel_err
+from test_oracle_step import frac_within
+
+pytestmark = pytest.mark.gpu
+
+
+def _nets():
+    from dvd_b200 import synthetic
+    from dvd_b200.third_party.MiDaS import MidasNet
+    return synthetic.seed_net_(MidasNet(non_negative=True, normalize_input=True), 0, 2000.0).eval()
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 96), (1, 224, 384)])
+def test_midas_engine_forward_backward_vs_oracle(shape):
+    from oracle import depth_nets
+    N, H, W = shape
+    net = _nets()
+    x = torch.rand(N, 3, H, W, generator=torch.Generator().manual_seed(3))
+    sd = {k: (v.detach().clone().requires_grad_() if (v.dtype.is_floating_point and 'running' not in k) else v)
+          for k, v in net.state_dict().items()}
+    ref = depth_nets.midas_forward(sd, x)
+    cot = torch.randn(ref.shape, generator=torch.Generator().manual_seed(4)) * 1e-3
+    (ref * cot).sum().backward()
+    net = net.cuda()
+    with torch.no_grad():
+        d_inf = net(x.cuda())
+    assert rel_err(d_inf, ref) < 1e-3, rel_err(d_inf, ref)
+    d = net(x.cuda())
+    assert d.requires_grad and torch.equal(d.detach(), d_inf)
+    (d * cot.cuda()).sum().backward()
+    worst = (0.0, None)
+    report = []
+    for k, p in net.named_parameters():
+        gref = sd[k].grad
+        if gref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        fw = frac_within(p.grad.reshape(gref.shape), gref, 1e-2)
+        me = rel_err(p.grad.reshape(gref.shape), gref)
+        report.append((k, fw, me))
+        if 1 - fw > worst[0]:
+            worst = (1 - fw, k)
+    bad = [r for r in report if r[1] < 0.97 or r[2] > 0.1]
+    assert not bad, bad[:10]
+    # aggregate over the whole net: relative L2 error of the gradient
+    num = sum(float(((p.grad.reshape(sd[k].grad.shape).double().cpu() - sd[k].grad.double()) ** 2).sum()) for k, p in net.named_parameters()
+              if sd[k].grad is not None)
+    den = sum(float((sd[k].grad.double() ** 2).sum()) for k, p in net.named_parameters() if sd[k].grad is not None)
+    assert (num / den) ** 0.5 < 5e-3, (num / den) ** 0.5
+
+
+def test_midas_engine_uses_no_library_kernels():
+    """kineto trace of one training forward + backward: no cuDNN / cutlass / ATen convolution or batch-norm kernel."""
+    from torch.profiler import ProfilerActivity, profile
+    net = _nets().cuda()
+    x = torch.rand(2, 3, 64, 96, device='cuda')
+    net(x).sum().backward()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        net(x).sum().backward()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    lib = [n for n in names if any(s in n.lower() for s in ('cudnn', 'cutlass', 'xmma', 'implicit_gemm', 'batch_norm', 'convolve'))]
+    assert not lib, lib
+    assert any('conv2d_tc_kernel' in n for n in names) and any('conv_wgrad_kernel' in n for n in names)

@@ -50,26 +50,3 @@ def test_upsample2x_matches_torch(C, H, W, align):
     (yr * cot).sum().backward()
     assert rel_err(y, yr) < 2e-6
     assert rel_err(g, x.grad) < 2e-5
-
-
-def test_midas_gpu_channels_last_matches_cpu():
-    from dvd_b200 import synthetic
-    from dvd_b200.third_party.MiDaS import MidasNet
-    torch.backends.cudnn.allow_tf32 = False
-    net = synthetic.seed_net_(MidasNet(non_negative=True, normalize_input=True), 0, 2000.0).eval()
-    x = torch.rand(2, 3, 64, 96)
-    ref = net(x)
-    ref.sum().backward()
-    gref = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
-    for p in net.parameters():
-        p.grad = None
-    net = net.cuda()
-    out = net(x.cuda())
-    out.sum().backward()
-    assert rel_err(out, ref) < 1e-4
-    worst = 0.0
-    for k, p in net.named_parameters():
-        if k in gref:
-            e = float(((p.grad.cpu() - gref[k]).abs() <= 5e-3 * gref[k].abs().max()).float().mean())
-            worst = max(worst, 1 - e)
-    assert worst < 0.02      # ReLU-kink flips only
