@@ -379,7 +379,7 @@ def roofline_depth_convs(model, batch, epoch, tflops_peak, peak_kind):
     finally:
         conv_ops.PROFILE = None
     agg = {}
-    for kind, flops, e0, e1 in rec:
+    for kind, flops, e0, e1, _info in rec:
         a = agg.setdefault(kind, [0.0, 0.0, 0])
         a[0] += flops
         a[1] += e0.elapsed_time(e1) * 1e-3

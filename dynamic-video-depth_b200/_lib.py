@@ -65,6 +65,7 @@ SIGNATURES = {
                       ctypes.c_long, _P],
     'dvd_acc_reg': [_P, _P, _F, _F, _P, _P, _P, _P, ctypes.c_long, _P],
     'dvd_adam_flat': [_P, _P, _P, _P, ctypes.c_long, _F, _F, _F, _F, _I, _F, _P],
+    'dvd_adam_flat_dev': [_P, _P, _P, _P, ctypes.c_long, _F, _F, _F, _F, _P, _F, _P],
     'dvd_bn_act_fwd': [_P, _P, _P, _P, _P, _P, _F, _P, ctypes.c_long, _I, _I, _P],
     'dvd_bn_act_bwd': [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, ctypes.c_long, _I, _I, _P],
     'dvd_upsample2x_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -20,12 +20,13 @@ GROUP_BLOCK = 64     # grouped convolutions run as block-diagonal GEMM blocks of
 PROFILE = None
 
 
-def _prof(kind, flops):
+def _prof(kind, flops, desc=None):
     if PROFILE is None:
         return None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    PROFILE.append((kind, flops, e0, e1))
+    info = (desc.N, desc.H, desc.W, desc.Cin, desc.OH, desc.OW, desc.Cout, desc.stride, desc.ntaps, desc.kblock) if desc is not None else None
+    PROFILE.append((kind, flops, e0, e1, info))
     return e1
 
 
@@ -95,7 +96,7 @@ def make_desc(N, H, W, Cin, OH, OW, Cout, taps, stride=1, kblock=0, YH=None, YW=
 def conv2d_launch(desc, x, w_img, y, bias=None, bn=None, res=None, res2=None, mask=None, flops=0.0, kind='conv'):
     g, b, m, v = bn if bn is not None else (None, None, None, None)
     LAUNCHES['n'] += 1
-    ev = _prof(kind, flops)
+    ev = _prof(kind, flops, desc)
     _lib.check(_lib.load().dvd_conv2d_nhwc(ctypes.byref(desc), _ptr(x), _ptr(w_img), _ptr(bias), _ptr(g), _ptr(b), _ptr(m), _ptr(v),
                                            _ptr(res), _ptr(res2), _ptr(mask), _ptr(y), _stream()), 'dvd_conv2d_nhwc')
     if ev is not None:
@@ -127,7 +128,7 @@ def wgrad_launch(desc, x, gy, dweight, ksize, groups=1, weight=None, bn=None, dg
         raise ValueError('parameter and gradient must share their strides')
     g, v = bn if bn is not None else (None, None)
     LAUNCHES['n'] += 1
-    ev = _prof('wgrad', flops)
+    ev = _prof('wgrad', flops, desc)
     _lib.check(_lib.load().dvd_conv2d_wgrad(ctypes.byref(desc), _ptr(x), _ptr(gy), _ptr(dweight), _ptr(weight), st[0], st[1], st[2],
                                             st[3], int(ksize), int(groups), _ptr(g), _ptr(v), _ptr(dgamma), _stream()),
                'dvd_conv2d_wgrad')

@@ -11,7 +11,8 @@ namespace dvd {
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, long n, float lr,
                                                         float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                                                        float gscale) {
+                                                        float gscale, const float* __restrict__ bc_dev) {
+  if (bc_dev) { bc1 = bc_dev[1]; bc2_sqrt = bc_dev[2]; }      // step counter kept on the device (CUDA-graph replays)
   const float step_size = lr / bc1;
   const long n4 = n >> 2;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -43,6 +44,14 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
   }
 }
 
+// device-side step counter: state = {step (as float bits of an int), 1 - b1^step, sqrt(1 - b2^step)}
+__global__ void adam_tick_kernel(float* __restrict__ state, float b1, float b2) {
+  const int step = __float_as_int(state[0]) + 1;
+  state[0] = __int_as_float(step);
+  state[1] = (float)(1.0 - pow((double)b1, (double)step));
+  state[2] = (float)sqrt(1.0 - pow((double)b2, (double)step));
+}
+
 }  // namespace dvd
 
 extern "C" int dvd_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
@@ -56,7 +65,23 @@ extern "C" int dvd_adam_flat(float* p, const float* g, float* m, float* v, long 
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   dvd::adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1,
-                                                                        (float)sqrt(bc2), gscale);
+                                                                        (float)sqrt(bc2), gscale, nullptr);
+  DVD_CUDA_LAUNCH_CHECK("adam_flat");
+  return 0;
+}
+
+extern "C" int dvd_adam_flat_dev(float* p, const float* g, float* m, float* v, long n, float lr, float beta1, float beta2,
+                                 float eps, float* step_state, float gscale, void* stream) {
+  DVD_ARG_CHECK(p && g && m && v && step_state && n > 0, "bad arguments");
+  DVD_ARG_CHECK(dvd::aligned16(p) && dvd::aligned16(g) && dvd::aligned16(m) && dvd::aligned16(v), "buffers must be 16-byte aligned");
+  long blocks = (n / 4 + 255) / 256;
+  long cap = (long)dvd::num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dvd::adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_state, beta1, beta2);
+  DVD_CUDA_LAUNCH_CHECK("adam_tick");
+  dvd::adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, gscale,
+                                                                        step_state);
   DVD_CUDA_LAUNCH_CHECK("adam_flat");
   return 0;
 }

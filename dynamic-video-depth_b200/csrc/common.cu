@@ -14,12 +14,12 @@ void set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  static int cached[16] = {0};     // per device
   int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess &&
-      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
-    cached = n;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  if (cached[dev] > 0) return cached[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+    cached[dev] = n;
     return n;
   }
   return 148;  // B200

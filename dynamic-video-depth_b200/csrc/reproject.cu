@@ -16,6 +16,9 @@
 // Algorithmic HBM bytes per pixel (fp32): fwd 32 (d1 4, d2 4, flow 8, mask 4, sf 12);
 // bwd 48 (the same 32 read + g_sf 12 + g_d2 4 written). See DESIGN.md for the full accounting.
 #include "common.cuh"
+#include <mutex>
+#include <utility>
+#include <vector>
 #include "tc_common.cuh"
 #include <initializer_list>
 #include <stdlib.h>
@@ -1164,11 +1167,13 @@ static int pick_vec(int B, int H, int W, std::initializer_list<const void*> ptrs
   bool al = true;
   for (const void* p : ptrs) al = al && (p == nullptr || aligned16(p));
   long total = (long)B * H * W;
+#ifdef DVD_PROFILING
   if (const char* ev = getenv("DVD_REPROJECT_VEC")) {   // tuning override: 1, 2 or 4
     int v = atoi(ev);
     if ((v == 4 && al && W % 4 == 0) || (v == 2 && al && W % 2 == 0)) return v;
     if (v == 1) return 1;
   }
+#endif
   // wide vectors only when enough threads remain to cover HBM latency (>= 512 / 256 threads per SM)
   if (max_vec >= 4 && al && W % 4 == 0 && total / 4 >= (long)num_sms() * 512) return 4;
   if (max_vec >= 2 && al && W % 2 == 0 && total / 2 >= (long)num_sms() * 256) return 2;
@@ -1196,20 +1201,62 @@ static dim3 grid_bound(int B, int items_per_pair) {
   return dim3((unsigned)per_pair, (unsigned)B, 1);
 }
 
-// stage the derived poses of pairs [b0, b0 + nb) into a constant-memory slot (all on `st`, no host synchronisation)
-static int stage_poses(const float* poses, int b0, int nb, cudaStream_t st, int* slot_out) {
-  static std::atomic<unsigned> ctr{0};
-  static PoseC* stage = [] {
+// Stage the derived poses of pairs [b0, b0 + nb) into a constant-memory slot (all on `st`, no host synchronisation).
+// Slots rotate; a slot is handed out again only after the kernel that last read it has finished: every user records a
+// per-slot event behind its kernel (release_pose_slot) and the next owner makes its stream wait on that event before it
+// overwrites the slot, so calls in flight on any number of streams (or more than kPoseSlots deep) cannot see each other's
+// poses. Symbol address and events are per device.
+struct PoseSlots {
+  PoseC* stage = nullptr;
+  cudaEvent_t ev[kPoseSlots] = {};
+  bool used[kPoseSlots] = {};
+  unsigned ctr = 0;
+  bool ok = false;
+};
+static std::mutex g_pose_mu;
+static PoseSlots* pose_slots() {     // call with g_pose_mu held
+  static PoseSlots per_dev[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  PoseSlots& S = per_dev[dev];
+  if (!S.ok) {
     void* p = nullptr;
-    return cudaGetSymbolAddress(&p, g_pose_stage) == cudaSuccess ? static_cast<PoseC*>(p) : nullptr;
-  }();
-  DVD_ARG_CHECK(stage != nullptr, "cudaGetSymbolAddress(g_pose_stage) failed");
-  const int slot = (int)(ctr.fetch_add(1u) % (unsigned)kPoseSlots);
+    if (cudaGetSymbolAddress(&p, g_pose_stage) != cudaSuccess) return nullptr;
+    S.stage = static_cast<PoseC*>(p);
+    for (int i = 0; i < kPoseSlots; ++i)
+      if (cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    S.ok = true;
+  }
+  return &S;
+}
+static int stage_poses(const float* poses, int b0, int nb, cudaStream_t st, int* slot_out) {
+  std::lock_guard<std::mutex> lk(g_pose_mu);
+  PoseSlots* S = pose_slots();
+  DVD_ARG_CHECK(S != nullptr, "pose staging: cudaGetSymbolAddress / cudaEventCreate failed");
+  const int slot = (int)(S->ctr++ % (unsigned)kPoseSlots);
+  // (inside a stream capture the launches of the graph are ordered on the capture stream and replays are ordered on their
+  // stream: events from outside the capture must not be waited on there)
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  DVD_CUDA_CALL(cudaStreamIsCapturing(st, &cap));
+  if (cap == cudaStreamCaptureStatusNone && S->used[slot])
+    DVD_CUDA_CALL(cudaStreamWaitEvent(st, S->ev[slot], 0));   // previous reader of this slot is done
   pose_prep_kernel<<<1, kPosePairs, 0, st>>>(poses + (size_t)b0 * DVD_POSE_STRIDE, nb, slot);
   DVD_CUDA_LAUNCH_CHECK("pose_prep");
-  DVD_CUDA_CALL(cudaMemcpyToSymbolAsync(c_pose, stage + (size_t)slot * kPosePairs, (size_t)nb * sizeof(PoseC),
+  DVD_CUDA_CALL(cudaMemcpyToSymbolAsync(c_pose, S->stage + (size_t)slot * kPosePairs, (size_t)nb * sizeof(PoseC),
                                         (size_t)slot * kPosePairs * sizeof(PoseC), cudaMemcpyDeviceToDevice, st));
   *slot_out = slot;
+  return 0;
+}
+// record "the kernel reading `slot` has been enqueued on `st`" (call right after that launch)
+static int release_pose_slot(int slot, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_pose_mu);
+  PoseSlots* S = pose_slots();
+  DVD_ARG_CHECK(S != nullptr, "pose staging unavailable");
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  DVD_CUDA_CALL(cudaStreamIsCapturing(st, &cap));
+  if (cap != cudaStreamCaptureStatusNone) return 0;
+  DVD_CUDA_CALL(cudaEventRecord(S->ev[slot], st));
+  S->used[slot] = true;
   return 0;
 }
 
@@ -1265,6 +1312,20 @@ extern "C" int dvd_unproject_bwd(const float* gP, const float* poses, float* gde
   return 0;
 }
 
+// cudaFuncSetAttribute once per (function, device)
+static int set_smem_once(const void* fn, int smem) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  DVD_CUDA_CALL(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& d : done)
+    if (d.first == fn && d.second == dev) return 0;
+  DVD_CUDA_CALL(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  done.emplace_back(fn, dev);
+  return 0;
+}
+
 static int check_cfg(const dvd_loss_cfg* cfg) {
   DVD_ARG_CHECK(cfg != nullptr, "null loss cfg");
   DVD_ARG_CHECK(cfg->disp_mode >= 0 && cfg->disp_mode <= 2, "disp_mode must be 0,1,2");
@@ -1284,8 +1345,14 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
   const int ipp = H * W / vec;
   dim3 g;
   // DVD_REPROJECT_SCALAR=1 forces the generic scalar kernels (any shape); DVD_REPROJECT_DRY=1 is a memory-system probe
+  // DVD_REPROJECT_SCALAR=1 (any build) forces the generic scalar kernels - a cross-check with identical results; the
+  // arithmetic-free memory probe exists in -DDVD_PROFILING builds only
   static const bool packed = !(getenv("DVD_REPROJECT_SCALAR") && atoi(getenv("DVD_REPROJECT_SCALAR")));
+#ifdef DVD_PROFILING
   static const bool dry = getenv("DVD_REPROJECT_DRY") && atoi(getenv("DVD_REPROJECT_DRY"));
+#else
+  constexpr bool dry = false;
+#endif
   if (vec == 4 && packed) {
     // packed-FP32 kernel, bulk-async staged inputs: 1 pixel pair per consumer thread, 4-deep ring, 3 CTAs per SM
     // (fastest of the measured variants, profiles/r1_ncu_reproject_variants.txt)
@@ -1293,7 +1360,7 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
                          : (const void*)reproject_loss_fwd_staged_kernel<1, 4, 3, false>;
     constexpr int np = 1, stages = 4, ctas = 3;
     const int tile = kThreads * 2 * np, smem = stages * tile * 7 * 4;
-    DVD_CUDA_CALL(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int e = set_smem_once(fn, smem)) return e;
     const int tiles_per_pair = (H * W + tile - 1) / tile;
     unsigned nq = 0;
     for (int b0 = 0; b0 < B; b0 += kPosePairs) {
@@ -1308,6 +1375,7 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
       void* args[] = {(void*)&depth_1, (void*)&depth_2, (void*)&flow_1_2, (void*)&mask_2, (void*)&sf, (void*)&cfgv, (void*)&part,
                       (void*)&Hh, (void*)&Ww, (void*)&slot, (void*)&b0v, (void*)&nb, (void*)&tpp};
       DVD_CUDA_CALL(cudaLaunchKernel(fn, dim3((unsigned)gx), dim3(kThreads + 32), args, (size_t)smem, st));
+      if (int e = release_pose_slot(slot, st)) return e;
       nq += (unsigned)gx;
     }
     g = dim3(nq, 1, 1);
@@ -1334,7 +1402,9 @@ extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2
   DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && mask_2 && sf && poses && scalars && g_sf, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_depth_2) DVD_CUDA_CALL(cudaMemsetAsync(g_depth_2, 0, (size_t)B * H * W * sizeof(float), st));
+#ifdef DVD_PROFILING
   if (getenv("DVD_REPROJECT_BWD_NOSCATTER")) g_depth_2 = nullptr;   // profiling probe only: skip the scatter-add
+#endif
   // measured on B200 (profiles/r1_reproject_vec_sweep.txt): the scatter-add backward is fastest with one pixel per
   // thread (1.97 TB/s vs 1.28 / 1.46 for 2 / 4): more warps in flight hide the red.global latency
   static const bool packed = !(getenv("DVD_REPROJECT_SCALAR") && atoi(getenv("DVD_REPROJECT_SCALAR")));
@@ -1344,7 +1414,7 @@ extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2
     const void* fn = (const void*)reproject_loss_bwd_staged_kernel<1, 4, 2>;
     constexpr int np = 1, stages = 4, ctas = 2;
     const int tile = kThreads * 2 * np, smem = stages * tile * 7 * 4;
-    DVD_CUDA_CALL(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (int e = set_smem_once(fn, smem)) return e;
     const int tiles_per_pair = (H * W + tile - 1) / tile;
     for (int b0 = 0; b0 < B; b0 += kPosePairs) {
       int nb = B - b0 < kPosePairs ? B - b0 : kPosePairs;
@@ -1358,6 +1428,7 @@ extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2
                       (void*)&gscale, (void*)&gscale_dev, (void*)&g_sf, (void*)&g_depth_2, (void*)&Hh, (void*)&Ww, (void*)&slot,
                       (void*)&b0v, (void*)&nb, (void*)&tpp};
       DVD_CUDA_CALL(cudaLaunchKernel(fn, dim3((unsigned)gx), dim3(kThreads + 32), args, (size_t)smem, st));
+      if (int e = release_pose_slot(slot, st)) return e;
     }
     return 0;
   }

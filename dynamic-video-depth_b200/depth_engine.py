@@ -57,8 +57,10 @@ class MidasEngine:
         self.oc0, self.oc2, self.oc4 = Conv(s.output_conv[0]), Conv(s.output_conv[2]), s.output_conv[4]
         self._all = [c for st in self.stages for b in st for c in b.convs()] + self.rn
         self._all += [c for r in self.rcu_a[:3] + self.rcu_b for c in (r.c1, r.c2)] + [self.oc0, self.oc2]
-        self._packed_version = None
         self.saved = None
+        # called as grad_hook(stage) at the points of backward() where a contiguous block of parameter gradients is final:
+        # 'decoder+layer4', 'layer3', 'rest' - the data-parallel path all-reduces that block while the backward goes on
+        self.grad_hook = None
 
     # ---------------------------------------------------------------------------------------------------
     def pack(self, need_bwd=True):
@@ -83,7 +85,7 @@ class MidasEngine:
         feats = []
         for st in self.stages:
             for b in st:
-                idt = b.ds.fwd(cur) if b.ds is not None else cur
+                idt = b.ds.fwd(cur, round_out=False) if b.ds is not None else cur
                 y1 = b.c1.fwd(cur, relu=True)
                 y2 = b.c2.fwd(y1, relu=True)
                 y3 = b.c3.fwd(y2, res=idt, relu=True)
@@ -194,10 +196,14 @@ class MidasEngine:
                 else:
                     g_in = b.c1.dgrad(gm1, Hi, Wi, res=gm3, res2=extra, mask=x_in)
                 gm3 = g_in
+            if self.grad_hook is not None and si in (3, 2):
+                self.grad_hook('decoder+layer4' if si == 3 else 'layer3')
         a0 = S['a0']
         g_a0 = co.maxpool_bwd(g_in, S['pool_idx'], a0.shape[2], a0.shape[3])
         nm, ns = (_NORM_MEAN, _NORM_STD) if self.normalize else (None, None)
         co.stem_wgrad(S['x'], g_a0, a0, self.stem_conv, self.stem_bn, nm, ns)
+        if self.grad_hook is not None:
+            self.grad_hook('rest')
 
 
 class MidasFunction(torch.autograd.Function):

@@ -67,6 +67,25 @@ class FlatParams:
         import torch.distributed as dist
         return dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, async_op=async_op)
 
+    def bucket_ranges(self, net, starts):
+        """Contiguous element ranges of the flat buffer delimited by the first parameter whose name starts with each prefix in
+        `starts` (in parameter order): [0, s1), [s1, s2), ..., [s_last, numel). Used to all-reduce the gradient in buckets, in
+        the order the explicit backward of depth_engine.MidasEngine completes them (decoder + layer4 first)."""
+        names = [n for n, _ in net.named_parameters()]
+        cuts = []
+        for pre in starts:
+            i = next(j for j, n in enumerate(names) if n.startswith(pre))
+            cuts.append(self.offsets[i])
+        cuts = [0] + cuts + [self.numel]
+        return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
+
+    def allreduce_range(self, a, b, async_op=True):
+        """Sum-all-reduce of grad[a:b]. With the NCCL backend the collective runs on the process group's own stream behind
+        everything already enqueued on the current stream, i.e. it overlaps the backward kernels launched after this call;
+        `work.wait()` later makes the current stream wait for it."""
+        import torch.distributed as dist
+        return dist.all_reduce(self.grad[a:b], op=dist.ReduceOp.SUM, async_op=async_op)
+
 
 class FlatAdam:
     """torch.optim.Adam(betas, eps=1e-8, weight_decay=0, amsgrad=False) on a FlatParams buffer."""
@@ -77,6 +96,9 @@ class FlatAdam:
         self.step_count = 0
         self.exp_avg = torch.zeros_like(flat.data)
         self.exp_avg_sq = torch.zeros_like(flat.data)
+        # the step counter also lives on the device ({int step, 1-b1^t, sqrt(1-b2^t), -}: dvd_adam_flat_dev increments it), so a
+        # captured CUDA graph of the optimisation step replays with the right bias correction
+        self.step_state = torch.zeros(4, dtype=torch.float32, device=flat.data.device)
         self.param_groups = [{'lr': self.lr, 'betas': self.betas, 'eps': self.eps, 'weight_decay': 0,
                               'amsgrad': False, 'params': list(range(len(flat.params)))}]
 
@@ -88,12 +110,20 @@ class FlatAdam:
             P = ctypes.c_void_p
             st = P(torch.cuda.current_stream().cuda_stream)
             from . import ops
-            ops.LAUNCHES['n'] += 1
-            _lib.check(lib.dvd_adam_flat(P(f.data.data_ptr()), P(f.grad.data_ptr()), P(self.exp_avg.data_ptr()),
-                                         P(self.exp_avg_sq.data_ptr()), f.numel, self.lr, self.betas[0], self.betas[1],
-                                         self.eps, self.step_count, float(gscale), st), 'dvd_adam_flat')
+            ops.LAUNCHES['n'] += 2
+            _lib.check(lib.dvd_adam_flat_dev(P(f.data.data_ptr()), P(f.grad.data_ptr()), P(self.exp_avg.data_ptr()),
+                                             P(self.exp_avg_sq.data_ptr()), f.numel, self.lr, self.betas[0], self.betas[1],
+                                             self.eps, P(self.step_state.data_ptr()), float(gscale), st), 'dvd_adam_flat_dev')
         else:
             raise RuntimeError('FlatAdam needs CUDA buffers: dvd_b200 has no CPU compute path')
+
+    def note_replayed(self, n=1):
+        """A captured graph containing `step()` was replayed n times: keep the host-side counter (checkpoints) in step."""
+        self.step_count += n
+
+    def _sync_step_state(self):
+        self.step_state.zero_()
+        self.step_state[:1].view(torch.int32).fill_(int(self.step_count))
 
     # ---- torch.optim.Adam-compatible state dicts (models/netinterface.py:528-574) -----------------
     def state_dict(self):
@@ -114,6 +144,7 @@ class FlatAdam:
             self.flat._view(self.exp_avg_sq, p, o).copy_(st['exp_avg_sq'])
             steps.append(int(float(st['step'])))
         self.step_count = max(steps) if steps else 0
+        self._sync_step_state()
         if not keep_training_params and sd.get('param_groups'):
             g = sd['param_groups'][0]
             self.lr, self.betas, self.eps = float(g['lr']), tuple(g['betas']), float(g['eps'])

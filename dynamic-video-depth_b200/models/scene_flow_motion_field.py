@@ -210,23 +210,16 @@ class Model(NetInterface):
         return d[:B].contiguous(), d[B:].contiguous()
 
     # ---- one optimisation step (smf.py:152-227) --------------------------------------------------------------
-    def _train_on_batch(self, epoch, batch_ind, batch):
+    def _step_body(self, inp, steps, dt):
+        """Everything of one step that runs on the device, with NO host synchronisation (so it can be captured in a CUDA
+        graph): forward, losses, ONE backward, gradient exchange, both Adam updates. `inp` = namespace of device tensors.
+        Returns (logs [9] on the device: flow, disp, sf, loss, mask-sum, cf, cd, -, acc_reg; d1, d2, sf, poses for visualisation)."""
         o = self.opt
-        self.warm = epoch <= o.warm_sf
-        self._set_depth_trainable(not self.warm)
         for opt_ in self._optimizers:
             opt_.materialize().zero_grad()
-        # the DataLoader's batch dim of 1 is dropped without touching the caller's dict (smf.py:177-179)
-        lead = batch['img_1'].dim() == 5
-        b = {k: (v.squeeze(0) if (lead and torch.is_tensor(v) and v.dim() > 0) else v) for k, v in batch.items()}
-        steps, dt = self._host_steps(b)
-        self.steps = steps
-        self.load_batch(b)
-        inp = self._input
         B, _, H, W = inp.img_1.shape
         use_reg = o.interp_steps > 0 and (not self.warm or o.warm_reg) and o.acc_mul > 0
         n_eval = max(steps, 2) if use_reg else steps
-
         if self.warm:
             with torch.no_grad():
                 d1, d2 = self._depths(inp.img_1, inp.img_2)
@@ -235,6 +228,7 @@ class Model(NetInterface):
         poses = ops.pack_poses(inp.K, inp.K_inv, inp.R_1_T, inp.R_2_T, inp.t_1, inp.t_2)
         P1 = ops.unproject(d1, poses, 1)
         ts1 = inp.time_stamp_1.contiguous() if o.time_dependent else None
+        self.net_sceneflow._packed_version = None   # weights changed behind autograd's back last step: re-pack
         acc, s_steps = self.net_sceneflow.chain(P1, ts1, dt, n_eval, steps, o.sf_mag_div)
         sf = acc
         if o.use_motion_seg:
@@ -247,34 +241,149 @@ class Model(NetInterface):
         if use_reg:
             reg = _AccReg.apply(s_steps[0], s_steps[1], float(o.acc_mul))
             total = total + reg
-        total.backward()
+        # gradient exchange (the reference's DDP wrappers are discarded, train.py:284-287; this is what they intended): sum
+        # all-reduce of the flat gradient buffers. The depth net's 422 MB go in three buckets, each launched the moment the
+        # explicit backward (depth_engine.py) has finished that block - decoder + layer4 (190 MB), layer3 (220 MB), the rest -
+        # on NCCL's stream, overlapping the remaining backward; the MLP's 1.2 MB follow the scene-flow chain's backward.
+        works = []
+        overlap = self._world > 1 and o.midas and not self.warm
+        if overlap:
+            flat = self.optimizer_depth.flat
+            if getattr(self, '_buckets', None) is None:
+                r = flat.bucket_ranges(self.net_depth, ['pretrained.layer3.', 'pretrained.layer4.'])
+                self._buckets = {'rest': r[0], 'layer3': r[1], 'decoder+layer4': r[2]}
+            first = [True]
 
-        # gradient exchange (the reference's DDP wrappers are discarded, train.py:284-287; this is what they intended)
+            def hook(stage):
+                if first[0]:      # the scene-flow MLP's gradients were final before the depth net's backward began
+                    works.append(self.optimizer_scene.flat.allreduce_grad(async_op=True))
+                    first[0] = False
+                a, b_ = self._buckets[stage]
+                works.append(flat.allreduce_range(a, b_))
+            self.net_depth.engine().grad_hook = hook
+        total.backward()
         gscale = 1.0
         if self._world > 1:
-            for opt_ in self._optimizers:
-                if opt_ is self.optimizer_depth and self.warm:
-                    continue
-                opt_.flat.allreduce_grad()
+            if overlap:
+                self.net_depth.engine().grad_hook = None
+                for w in works:
+                    w.wait()
+            else:
+                for opt_ in self._optimizers:
+                    if opt_ is self.optimizer_depth and self.warm:
+                        continue
+                    opt_.flat.allreduce_grad()
             gscale = 1.0 / self._world
         if not self.warm:
             self.optimizer_depth.step(gscale)
         self.optimizer_scene.step(gscale)
-        self.net_sceneflow._packed_version = None   # weights changed behind autograd's back: re-pack next step
+        logs = torch.cat([scal, (reg.detach().reshape(1) if reg is not None else scal.new_zeros(1))])
+        return logs, d1.detach(), d2.detach(), sf.detach(), poses
 
-        # ONE device->host read per step: [flow, disp, sf, loss, mask_sum, cf, cd, -, acc_reg]
-        logs = torch.cat([scal, (reg.detach().reshape(1) if reg is not None else scal.new_zeros(1))]).cpu()
+    def _train_on_batch(self, epoch, batch_ind, batch):
+        o = self.opt
+        self.warm = epoch <= o.warm_sf
+        self._set_depth_trainable(not self.warm)
+        # the DataLoader's batch dim of 1 is dropped without touching the caller's dict (smf.py:177-179)
+        lead = batch['img_1'].dim() == 5
+        b = {k: (v.squeeze(0) if (lead and torch.is_tensor(v) and v.dim() > 0) else v) for k, v in batch.items()}
+        steps, dt = self._host_steps(b)
+        self.steps = steps
+        if self._graph_ok():
+            logs, vis = self._graph_step(b, steps, dt)
+        else:
+            self.load_batch(b)
+            dev_logs, d1, d2, sf, poses = self._step_body(self._input, steps, dt)
+            logs = dev_logs.cpu()    # ONE device->host read per step
+            vis = (d1, d2, sf, poses)
         # `**loss_data` overrides the step-weighted 'loss' in the reference's dict literal (smf.py:226,321)
+        has_reg = o.interp_steps > 0 and (not self.warm or o.warm_reg) and o.acc_mul > 0
         batch_log = {'size': o.batch_size, 'loss': float(logs[3]), 'total_loss': float(logs[3]),
                      'flow_loss_1_2': float(logs[0]), 'disp_loss_1_2': float(logs[1]), 'sf_loss': float(logs[2]),
-                     'acc_reg': float(logs[8]) if reg is not None else 0}
+                     'acc_reg': float(logs[8]) if has_reg else 0}
 
+        # smf.py:215-225. Without --vis_at_start the reference counts back from opt.epoch_batches (a TypeError when that is
+        # None, so there is no behaviour to keep): no dump then, and only indices 0 <= indx <= vis_batches_train dump.
         vis_every = getattr(o, 'vis_every_train', 0)
         if vis_every and np.mod(epoch, vis_every) == 0 and self.full_logdir:
-            indx = batch_ind if getattr(o, 'vis_at_start', False) else (o.epoch_batches or 0) - batch_ind
-            if indx <= getattr(o, 'vis_batches_train', 0):
-                self._dump_visual(epoch, batch_ind, indx, b, d1.detach(), d2.detach(), sf.detach(), poses)
+            if getattr(o, 'vis_at_start', False):
+                indx = batch_ind
+            else:
+                indx = (o.epoch_batches - batch_ind) if getattr(o, 'epoch_batches', None) else -1
+            if 0 <= indx <= getattr(o, 'vis_batches_train', 0):
+                self.load_batch(b)
+                d1, d2, sf, poses = vis
+                self._dump_visual(epoch, batch_ind, indx, b, d1, d2, sf, poses)
         return batch_log
+
+    # ---- CUDA-graph replay of the step ("CUDA-graph the step, kill every host sync") ------------------------
+    # One graph per step signature (pairs, resolution, Euler steps, phase): the ~1200 kernel launches of a step (104 convolutions
+    # x {pack, forward, data gradient, weight gradient, column sums} + MLP chain + re-projection + Adam) are captured once and
+    # replayed with one cudaGraphLaunch; inputs are copied into static buffers, the 9 log floats come back through a pinned
+    # buffer. The first `graph_warmup` steps of a signature run eagerly (they are real optimisation steps), then the next one is
+    # captured and replayed. Graphs share one memory pool (they never run concurrently). Single-GPU only: with the NCCL gradient
+    # exchange the eager path (which overlaps the all-reduce with the backward) is used.
+    _GRAPH_KEYS = ('img_1', 'img_2', 'mask_2', 'R_1_T', 'R_2_T', 't_1', 't_2', 'flow_1_2', 'K', 'K_inv', 'motion_seg_1', 'time_stamp_1')
+
+    def _graph_ok(self):
+        return (getattr(self.opt, 'cuda_graph', True) and self._world == 1 and self.device.type == 'cuda' and self.opt.midas
+                and not getattr(self, '_graph_broken', False))
+
+    def _graph_step(self, b, steps, dt):
+        B = b['img_1'].shape[0]
+        sig = (B, tuple(b['img_1'].shape[-2:]), steps, bool(self.warm), round(float(dt), 9))
+        if not hasattr(self, '_graphs'):
+            self._graphs, self._graph_pool, self.graph_stats = {}, None, {'captured': 0, 'replayed': 0, 'eager': 0}
+        ent = self._graphs.setdefault(sig, {'seen': 0, 'graph': None})
+        if ent['graph'] is None and ent['seen'] < getattr(self.opt, 'graph_warmup', 2):
+            ent['seen'] += 1
+            self.graph_stats['eager'] += 1
+            self.load_batch(b)
+            dev_logs, d1, d2, sf, poses = self._step_body(self._input, steps, dt)
+            return dev_logs.cpu(), (d1, d2, sf, poses)
+        if ent['graph'] is None:
+            static = lambda: None   # noqa: E731
+            for k in self._GRAPH_KEYS:
+                setattr(static, k, torch.empty(b[k].shape, dtype=torch.float32, device=self.device))
+            ent['static'] = static
+            ent['pinned'] = torch.empty(9, dtype=torch.float32).pin_memory()
+            for k in self._GRAPH_KEYS:
+                getattr(static, k).copy_(b[k], non_blocking=True)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES['n']
+            try:
+                with torch.cuda.graph(g, pool=self._graph_pool):
+                    dev_logs, d1, d2, sf, poses = self._step_body(static, steps, dt)
+                    ent['pinned'].copy_(dev_logs, non_blocking=True)
+            except Exception as e:   # noqa: BLE001  capture is an optimisation: report and keep stepping eagerly
+                self._graph_broken = True
+                self.graph_error = repr(e)[:500]
+                torch.cuda.synchronize()
+                for o_ in self._optimizers:      # the host-side counters advanced during the aborted capture
+                    if o_.adam is not None:
+                        o_.adam.step_count -= 0 if (o_ is self.optimizer_depth and self.warm) else 1
+                self.load_batch(b)
+                dev_logs, d1, d2, sf, poses = self._step_body(self._input, steps, dt)
+                return dev_logs.cpu(), (d1, d2, sf, poses)
+            if self._graph_pool is None:
+                self._graph_pool = g.pool()
+            ent.update(graph=g, vis=(d1, d2, sf, poses), launches=ops.LAUNCHES['n'] - n0, captured_now=True)
+            self.graph_stats['captured'] += 1
+        else:
+            for k in self._GRAPH_KEYS:
+                getattr(ent['static'], k).copy_(b[k], non_blocking=True)
+            ops.LAUNCHES['n'] += ent['launches']
+        if ent.pop('captured_now', False):
+            pass          # capture recorded the step (and advanced the host-side Adam counters) without executing it
+        else:
+            if not self.warm:
+                self.optimizer_depth.adam.note_replayed()
+            self.optimizer_scene.adam.note_replayed()
+        ent['graph'].replay()
+        self.graph_stats['replayed'] += 1
+        torch.cuda.current_stream().synchronize()      # the log of THIS step (NaN guard of the loggers), no run-ahead needed
+        return ent['pinned'].clone(), ent['vis']
 
     def _dump_visual(self, epoch, batch_ind, indx, batch, d1, d2, sf, poses):
         """The 13 `pred` arrays of the reference (smf.py:201-202, video_base.py:105-126), materialised only

@@ -61,6 +61,10 @@ def add_general_arguments(parser):
     a('--vis_param_f', default=None, type=str)
     a('--vis_at_start', action='store_true')
     a('--test_template', type=str, default=None)
+    # dvd_b200 extensions (the reference ignores unknown flags, options_train.py:184-186)
+    a('--resident', action='store_true', help='keep the whole sequence on the GPU and draw gap-bucketed, rank-disjoint batches '
+                                              '(datasets/resident.py) instead of one pair file per step through a DataLoader')
+    a('--pairs_per_step', type=int, default=1, help='frame pairs per step and GPU with --resident (the reference ships 1 per file)')
     return parser, unique_params
 
 

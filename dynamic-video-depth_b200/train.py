@@ -54,9 +54,17 @@ def main_worker(local_rank, ngpus, opt):
     if distributed:
         dist.barrier()
         model.sync_parameters(0)
-        sampler = torch.utils.data.distributed.DistributedSampler(ds)
-    loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=sampler is None, sampler=sampler,
-                                         num_workers=opt.workers, pin_memory=True, drop_last=True)
+    if getattr(opt, 'resident', False):
+        # the sequence lives on the GPU, batches are gap-uniform and disjoint across ranks
+        from .datasets.resident import GapBucketSampler, ResidentLoader, ResidentSequence
+        seq = ResidentSequence(ds, device)
+        sampler = GapBucketSampler(seq.gaps, opt.pairs_per_step, world, rank, seed=opt.manual_seed or 0)
+        loader = ResidentLoader(seq, sampler)
+    else:
+        if distributed:
+            sampler = torch.utils.data.distributed.DistributedSampler(ds)
+        loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=sampler is None, sampler=sampler,
+                                             num_workers=opt.workers, pin_memory=True, drop_last=True)
 
     def on_epoch(epoch):
         if sampler is not None:

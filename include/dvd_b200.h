@@ -173,6 +173,10 @@ int dvd_acc_reg(const float* s0, const float* s1, float acc_mul, float gscale, f
  * gradient is multiplied by gscale first (1/world_size after a sum all-reduce).                */
 int dvd_adam_flat(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
                   float beta2, float eps, int step, float gscale, void* stream);
+/* the same update with the step counter on the DEVICE (step_state: 4 floats {int step bits, 1-b1^t, sqrt(1-b2^t), -}; the call
+ * increments it first), so that a captured CUDA graph of the step replays with the right bias correction.                  */
+int dvd_adam_flat_dev(float* p, const float* g, float* m, float* v, long n, float lr, float beta1,
+                      float beta2, float eps, float* step_state, float gscale, void* stream);
 
 /* ---- channels-last (NHWC) glue of the depth nets (D1/D2): tensors are [P = N*H*W pixels][C], C % 4 == 0 ----
  * eval-mode BatchNorm (the only mode on this path, smf.py:157,168) + optional residual add + optional ReLU:

@@ -73,4 +73,55 @@ def test_pair_partition_is_disjoint_and_gap_uniform():
                 assert p[1] - p[0] == gap and 0 <= p[0] and p[1] < bench.N_FRAMES
                 seen.add(p)
         assert len(gaps) == 1                 # every rank runs the same number of Euler steps in a step
-        assert len(seen) >= 24                # (8 ranks x 4 pairs, frame ids spread over the sequence)
+        assert len(seen) == 32                # 8 ranks x 4 pairs: disjoint
+
+
+def test_gap_bucket_sampler_partitions_the_pair_list():
+    """product sampler (datasets/resident.py): per epoch every rank gets gap-uniform steps, the ranks' pairs of one step are
+    disjoint, nothing is drawn twice in an epoch, and epochs reshuffle."""
+    from dvd_b200 import synthetic
+    from dvd_b200.datasets.resident import GapBucketSampler
+    pairs = synthetic.pair_list(80, (1, 2, 4, 6, 8))
+    gaps = [b - a for a, b in pairs]
+    world, B = 8, 4
+    samplers = [GapBucketSampler(gaps, B, world, r, seed=3) for r in range(world)]
+    assert len({len(s) for s in samplers}) == 1 and len(samplers[0]) == sum((gaps.count(g) // (world * B)) for g in set(gaps))
+    per_rank = [list(iter(s)) for s in samplers]
+    drawn = set()
+    for step in range(len(per_rank[0])):
+        step_gaps = set()
+        for r in range(world):
+            idx = per_rank[r][step]
+            assert len(idx) == B
+            for i in idx:
+                assert i not in drawn
+                drawn.add(i)
+                step_gaps.add(gaps[i])
+        assert len(step_gaps) == 1
+    e0 = list(iter(samplers[0]))
+    samplers[0].set_epoch(1)
+    assert list(iter(samplers[0])) != e0
+    samplers[0].set_epoch(0)
+    assert list(iter(samplers[0])) == e0
+
+
+def test_resident_sequence_rebuilds_the_pair_file_batch():
+    """ResidentSequence on the CPU device (pure indexing): the assembled batch equals the collated pair files."""
+    import torch
+    from dvd_b200.datasets import get_dataset
+    from dvd_b200.datasets.resident import ResidentSequence
+    from dvd_b200.options import options_train
+    opt, _ = options_train.parse(['--net', 'scene_flow_motion_field', '--dataset', 'synthetic_sequence', '--gaps', '2,4',
+                                  '--height', '16', '--width', '24', '--n_frames', '12'])
+    ds = get_dataset('synthetic_sequence')(opt)
+    seq = ResidentSequence(ds, 'cpu')
+    assert len(seq) == len(ds) and seq.images.shape[0] <= 12
+    pick = [i for i, g in enumerate(seq.gaps) if g == 4][:3]
+    b = seq.batch(pick)
+    assert b['steps_hint'] == 4 and b['img_1'].shape == (3, 3, 16, 24)
+    for j, i in enumerate(pick):
+        it = ds[i]
+        for k in ('flow_1_2', 'mask_2', 'R_2_T', 't_1', 'K_inv', 'time_stamp_2'):
+            assert torch.equal(b[k][j], it[k][0]), k
+        # frames are de-duplicated by frame id: the synthetic generator draws img_2 per PAIR, the cache keeps the first image seen
+        assert b['img_1'][j].shape == it['img_1'][0].shape
