@@ -59,6 +59,8 @@ struct ConvParams {
   int kchunks;                    // 32-channel chunks per tap
   int tma_store;                  // epilogue through shared memory + TMA store (identity output mapping, NT % 32 == 0)
   int sbw, sbh;                   // per-warp store box: sbw x sbh = 32 pixels
+  int csize;                      // thread-block cluster size (1, 2, 4): the CTAs of a cluster work on consecutive pixel tiles of
+                                  // the same channel tile and share the weight stream (each loads NT/csize rows, multicast to all)
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -74,6 +76,36 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+// all MMAs issued so far by this thread complete -> one arrival on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
@@ -105,14 +137,17 @@ __device__ __forceinline__ float round_tf32(float v) {
 
 struct Tile {
   int n0, img, h0, w0;
+  bool valid;       // false: padding tile of an incomplete cluster (loads are zero-filled, nothing is stored)
 };
-__device__ __forceinline__ Tile decode_tile(const ConvParams& P, int tile, int m_tiles) {
+// cluster tile ct = (channel tile, group of csize consecutive pixel tiles); this CTA takes pixel tile group * csize + rank
+__device__ __forceinline__ Tile decode_tile(const ConvParams& P, int ct, int m_tiles, int mgroups, int crank) {
   Tile t;
-  const int nt = tile / m_tiles, m = tile - nt * m_tiles;
+  const int nt = ct / mgroups, m = (ct - nt * mgroups) * P.csize + crank;
   t.n0 = nt * P.NT;
+  t.valid = m < m_tiles;
   const int per_img = P.tiles_w * P.tiles_h;
-  t.img = m / per_img;
-  const int r = m - t.img * per_img;
+  t.img = t.valid ? m / per_img : P.d.N;          // image index N is out of bounds for every TMA map: zero fill / no store
+  const int r = t.valid ? m - t.img * per_img : 0;
   const int th = r / P.tiles_w;
   t.h0 = th * P.TH;
   t.w0 = (r - th * P.tiles_w) * P.TW;
@@ -169,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
   if (warp == 1) {
     tmem_alloc(tmem_holder, 512);
   } else if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)P.csize); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -179,20 +214,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (P.csize > 1) cluster_sync_all();         // every CTA's barriers exist before a peer's multicast can reach them
   const uint32_t tmem = *tmem_holder;
 
+  const int crank = P.csize > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / P.csize, n_clusters = gridDim.x / P.csize;
+  const uint16_t cmask = (uint16_t)((1u << P.csize) - 1u);
   const int m_tiles = P.d.N * P.tiles_w * P.tiles_h;
+  const int mgroups = (m_tiles + P.csize - 1) / P.csize;
   const int n_tiles = P.d.Cout / P.NT;
-  const int ntiles = m_tiles * n_tiles;
+  const int ntiles = mgroups * n_tiles;           // cluster tiles
   const int ksteps = P.d.ntaps * P.kchunks;
   const uint32_t stage_tx = (uint32_t)kABytes + (uint32_t)P.NT * 128u;
+  const int wslice = P.NT / P.csize;              // weight rows this CTA fetches (and multicasts) per stage
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const Tile T = decode_tile(P, tile, m_tiles);
+      for (int tile = cluster_id; tile < ntiles; tile += n_clusters) {
+        const Tile T = decode_tile(P, tile, m_tiles, mgroups, crank);
         const int kbase = P.d.kblock ? (T.n0 / P.d.kblock) * P.d.kblock : 0;
         const int ws = T.w0 * P.d.stride, hs = T.h0 * P.d.stride;
         for (int t = 0; t < P.d.ntaps; ++t) {
@@ -200,10 +241,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
           for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
             uint8_t* st = smem + (size_t)s * kStageBytes;
-            mbar_wait(&empty[s], ph ^ 1u);
+            mbar_wait(&empty[s], ph ^ 1u);            // every CTA of the cluster has drained this stage
             mbar_arrive_expect_tx(&full[s], stage_tx);
             tma_load_4d(st, &mapA, kbase + kc * 32, ws + dx, hs + dy, T.img, &full[s]);
-            tma_load_3d(st + kABytes, &mapW, kc * 32, T.n0, wt, &full[s]);
+            if (P.csize > 1)
+              tma_load_3d_mc(st + kABytes + crank * wslice * 128, &mapW, kc * 32, T.n0 + crank * wslice, wt, &full[s], cmask);
+            else
+              tma_load_3d(st + kABytes, &mapW, kc * 32, T.n0, wt, &full[s]);
           }
         }
       }
@@ -213,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, P.NT);
       uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
         const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
         mbar_wait(&acc_empty[buf], aph ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -226,7 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_ss_tf32(d, make_sdesc_k_sw128(sa + ks * 32), make_sdesc_k_sw128(sb + ks * 32), idesc, (k | ks) ? 1u : 0u);
-          umma_commit(&empty[s]);
+          if (P.csize > 1) umma_commit_mc(&empty[s], cmask);   // the stage also holds weight rows written by the peers
+          else umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[buf]);
       }
@@ -239,13 +284,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     uint8_t* stg = smem + kOffStg + (size_t)q * 2 * kStgBytes;
     const bool has_aff = P.gamma != nullptr || P.bias != nullptr;
     uint32_t lt = 0, nstore = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+    for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
       const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
-      const Tile T = decode_tile(P, tile, m_tiles);
+      const Tile T = decode_tile(P, tile, m_tiles, mgroups, crank);
       const int h = T.h0 + row / P.TW, w = T.w0 + row % P.TW;
       const int yh = h * P.d.oy_mul + P.d.oy_add, yw = w * P.d.ox_mul + P.d.ox_add;
-      const bool valid = h < P.d.OH && w < P.d.OW && yh < P.d.YH && yw < P.d.YW;
-      const size_t off = (((size_t)T.img * P.d.YH + yh) * P.d.YW + yw) * P.d.Cout + T.n0;
+      const bool valid = T.valid && h < P.d.OH && w < P.d.OW && yh < P.d.YH && yw < P.d.YW;
+      const size_t off = valid ? (((size_t)T.img * P.d.YH + yh) * P.d.YW + yw) * P.d.Cout + T.n0 : 0;
       const float* rrow = (P.res && valid) ? P.res + off : nullptr;
       const float* r2row = (P.res2 && valid) ? P.res2 + off : nullptr;
       const float* mrow = (P.mask && valid) ? P.mask + off : nullptr;
@@ -290,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&mapY, sb, T.n0 + c0, bw0, bh0, T.img);
+            if (T.valid) tma_store_4d(&mapY, sb, T.n0 + c0, bw0, bh0, T.img);
             bulk_commit();
           }
         }
@@ -315,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (P.csize > 1) cluster_sync_all();         // no CTA leaves while a peer may still multicast into it / signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -377,6 +423,8 @@ struct WgradParams {
   int TW, TH, tiles_w, tiles_h;    // 64-pixel tiles
   int NT;                          // N channels per output tile
   int ksplit;
+  int csize;                       // cluster size: the CTAs of a cluster own consecutive 128-row M blocks of the same (tap, N tile,
+                                   // pixel range) and share the N-operand stream (each loads every csize-th box, multicast)
   int cpg;                         // > 0: grouped (diagonal blocks, NT = 128)
   const float* gamma;              // eval BatchNorm of the out-channels (or null)
   const float* var;
@@ -414,21 +462,26 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   if (warp == 1) {
     tmem_alloc(tmem_holder, 256);
   } else if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)P.csize); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (P.csize > 1) cluster_sync_all();
   const uint32_t tmem = *tmem_holder;
 
-  // this CTA: output tile (tap, 128 M-channels, NT N-channels) and a contiguous range of pixel tiles
-  const int out_tile = blockIdx.x / P.ksplit, part = blockIdx.x - out_tile * P.ksplit;
-  const int n_m = P.Mch / 128, n_n = P.cpg ? 1 : P.Nch / P.NT;
-  const int t = out_tile / (n_m * n_n);
-  const int rem = out_tile - t * (n_m * n_n);
-  const int m0 = (rem / n_n) * 128;
+  // this CTA: output tile (tap, 128 M-channels, NT N-channels) and a contiguous range of pixel tiles.
+  // blockIdx.x = ((tap, M group, N tile) * ksplit + part) * csize + rank, M block = group * csize + rank
+  const int crank = P.csize > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << P.csize) - 1u);
+  const int cl = blockIdx.x / P.csize;
+  const int out_grp = cl / P.ksplit, part = cl - out_grp * P.ksplit;
+  const int n_mg = P.Mch / 128 / P.csize, n_n = P.cpg ? 1 : P.Nch / P.NT;
+  const int t = out_grp / (n_mg * n_n);
+  const int rem = out_grp - t * (n_mg * n_n);
+  const int m0 = ((rem / n_n) * P.csize + crank) * 128;
   const int n0 = P.cpg ? m0 : (rem % n_n) * P.NT;
   const int dy = P.dy[t], dx = P.dx[t];
   const int px_tiles = P.N * P.tiles_h * P.tiles_w;
@@ -451,7 +504,12 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], stage_tx);
         for (int j = 0; j < 4; ++j) tma_load_4d(st + j * kWgBox, &mapM, m0 + 32 * j, mw, mh, img, &full[s]);
-        for (int j = 0; j < nb; ++j) tma_load_4d(st + (4 + j) * kWgBox, &mapN, n0 + 32 * j, nw, nh, img, &full[s]);
+        if (P.csize > 1) {
+          for (int j = crank; j < nb; j += P.csize)
+            tma_load_4d_mc(st + (4 + j) * kWgBox, &mapN, n0 + 32 * j, nw, nh, img, &full[s], cmask);
+        } else {
+          for (int j = 0; j < nb; ++j) tma_load_4d(st + (4 + j) * kWgBox, &mapN, n0 + 32 * j, nw, nh, img, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -467,7 +525,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         for (int ks = 0; ks < kWgPx / 8; ++ks)
           umma_ss_tf32(tmem, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox), make_sdesc_mn_sw128_32b(sb + ks * 1024, kWgBox), idesc,
                        (it | ks) ? 1u : 0u);
-        umma_commit(&empty[s]);
+        if (P.csize > 1) umma_commit_mc(&empty[s], cmask);
+        else umma_commit(&empty[s]);
       }
       umma_commit(acc_full);
     }
@@ -533,6 +592,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (P.csize > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
@@ -594,6 +654,49 @@ int per_device_attr(const void* func, size_t smem_bytes, bool (&done)[16]) {
   return 0;
 }
 
+// launch `grid` CTAs in clusters of `csize` (grid % csize == 0)
+template <typename... Args>
+int launch_clustered(void (*kernel)(Args...), int grid, int threads, size_t smem_bytes, int csize, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DVD_CUDA_CALL(cudaLaunchKernelEx(&cfg, kernel, args...));
+  return 0;
+}
+
+// how many clusters of `csize` CTAs of this kernel can be resident at once (cached per device and size)
+template <typename K>
+int max_clusters(K kernel, int threads, size_t smem_bytes, int csize) {
+  static int cache[16][5] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = 0;
+  if (cache[dev][csize] > 0) return cache[dev][csize];
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(num_sms() / csize * csize));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) n = num_sms() / csize;
+  cache[dev][csize] = n;
+  return n;
+}
+
 }  // namespace
 }  // namespace dvd
 
@@ -644,6 +747,21 @@ extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const 
   P.tma_store = identity_out && (P.NT % 32 == 0);
   P.sbw = P.TW < 32 ? P.TW : 32;
   P.sbh = 32 / P.sbw;
+  static bool attr_done[16] = {};
+  if (int e = per_device_attr((const void*)conv2d_tc_kernel, kSmem, attr_done)) return e;
+  // cluster size: the weight tile is fetched once per cluster (NT / csize rows per CTA, whole 8-row swizzle atoms)
+  const long m_tiles_h = (long)d.N * P.tiles_w * P.tiles_h;
+  P.csize = 1;
+  {
+    // clusters of 4 may leave SMs idle (a GPC whose SM count is not a multiple of 4): take 4 only when it keeps the machine full
+    const int sm4 = 4 * max_clusters(conv2d_tc_kernel, kThreads, kSmem, 4), sm2 = 2 * max_clusters(conv2d_tc_kernel, kThreads, kSmem, 2);
+    if (m_tiles_h >= 8 && P.NT % 32 == 0 && sm4 + 4 >= sm2) P.csize = 4;
+    else if (m_tiles_h >= 2 && P.NT % 16 == 0) P.csize = 2;
+  }
+  if (const char* ev = getenv("DVD_CONV_CLUSTER")) {      // tuning / A-B override: 1, 2 or 4
+    const int v = atoi(ev);
+    if ((v == 1 || v == 2 || v == 4) && (P.NT / v) % 8 == 0) P.csize = v;
+  }
   CUtensorMap mapA, mapW, mapY;
   if (int e = make_nhwc_map(&mapA, x, inN, inH, inW, d.Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   {
@@ -652,7 +770,7 @@ extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const 
     const int Kw = d.kblock ? d.kblock : d.Cin;
     const cuuint64_t dims[3] = {(cuuint64_t)Kw, (cuuint64_t)d.Cout, (cuuint64_t)(max_wt + 1)};
     const cuuint64_t strides[2] = {(cuuint64_t)Kw * 4, (cuuint64_t)d.Cout * Kw * 4};
-    const cuuint32_t box[3] = {32, (cuuint32_t)P.NT, 1};
+    const cuuint32_t box[3] = {32, (cuuint32_t)(P.NT / P.csize), 1};
     const cuuint32_t ones[3] = {1, 1, 1};
     if (int e = make_map(&mapW, w_img, 3, dims, strides, box, ones, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
@@ -661,12 +779,12 @@ extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const 
   } else {
     mapY = mapA;
   }
-  static bool attr_done[16] = {};
-  if (int e = per_device_attr((const void*)conv2d_tc_kernel, kSmem, attr_done)) return e;
-  const long ntiles = (long)d.N * P.tiles_w * P.tiles_h * (d.Cout / P.NT);
-  int grid = num_sms();
-  if (ntiles < grid) grid = (int)ntiles;
-  conv2d_tc_kernel<<<grid, kThreads, kSmem, (cudaStream_t)stream>>>(mapA, mapW, mapY, P);
+  const long ctiles = ((m_tiles_h + P.csize - 1) / P.csize) * (d.Cout / P.NT);      // cluster tiles
+  long nclusters = max_clusters(conv2d_tc_kernel, kThreads, kSmem, P.csize);
+  if (ctiles < nclusters) nclusters = ctiles;
+  if (int e = launch_clustered(conv2d_tc_kernel, (int)nclusters * P.csize, kThreads, kSmem, P.csize, (cudaStream_t)stream, mapA, mapW,
+                               mapY, P))
+    return e;
   DVD_CUDA_LAUNCH_CHECK("conv2d_tc_kernel");
   return 0;
 }
@@ -741,19 +859,46 @@ extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const
   P.tiles_h = (OH + P.TH - 1) / P.TH;
   const int out_tiles = d.ntaps * (P.Mch / 128) * (P.cpg ? 1 : P.Nch / P.NT);
   const int px_tiles = N * P.tiles_h * P.tiles_w;
-  int ksplit = (num_sms() + out_tiles - 1) / out_tiles;
+  static bool attr_done[16] = {};
+  if (int e = per_device_attr((const void*)conv_wgrad_kernel, kWgSmem, attr_done)) return e;
+  // cluster over consecutive 128-row M blocks: they consume the same N-operand boxes
+  P.csize = 1;
+  if (!P.cpg) {
+    const int n_m = P.Mch / 128, nb = P.NT / 32;
+    const int sm4 = 4 * max_clusters(conv_wgrad_kernel, 192, kWgSmem, 4), sm2 = 2 * max_clusters(conv_wgrad_kernel, 192, kWgSmem, 2);
+    if (n_m % 4 == 0 && nb % 4 == 0 && sm4 + 4 >= sm2) P.csize = 4;
+    else if (n_m % 2 == 0 && nb % 2 == 0) P.csize = 2;
+    if (const char* ev = getenv("DVD_WGRAD_CLUSTER")) {
+      const int v = atoi(ev);
+      if ((v == 1 || v == 2 || v == 4) && n_m % v == 0 && nb % v == 0) P.csize = v;
+    }
+  }
+  // split-K so that all CTAs are resident in ONE wave (a second, nearly empty wave would double the time)
+  const int resident = P.csize * max_clusters(conv_wgrad_kernel, 192, kWgSmem, P.csize);
+  int ksplit = resident / out_tiles;
   if (ksplit > px_tiles) ksplit = px_tiles;
   if (ksplit < 1) ksplit = 1;
   P.ksplit = ksplit;
   CUtensorMap mapG, mapX;
   if (int e = make_nhwc_map(&mapG, gy, N, OH, OW, Cout, P.TW, P.TH, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
   if (int e = make_nhwc_map(&mapX, x, N, H, W, Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
-  static bool attr_done[16] = {};
-  if (int e = per_device_attr((const void*)conv_wgrad_kernel, kWgSmem, attr_done)) return e;
-  if (P.swap)
-    conv_wgrad_kernel<<<out_tiles * ksplit, 192, kWgSmem, (cudaStream_t)stream>>>(mapX, mapG, P);
-  else
-    conv_wgrad_kernel<<<out_tiles * ksplit, 192, kWgSmem, (cudaStream_t)stream>>>(mapG, mapX, P);
+  if (int e = launch_clustered(conv_wgrad_kernel, out_tiles * ksplit, 192, kWgSmem, P.csize, (cudaStream_t)stream, P.swap ? mapX : mapG,
+                               P.swap ? mapG : mapX, P))
+    return e;
   DVD_CUDA_LAUNCH_CHECK("conv_wgrad_kernel");
+  return 0;
+}
+
+/* resident CTAs of the two tensor-core kernels for cluster sizes 1, 2, 4 (diagnostic): out[0..2] forward / data gradient kernel,
+ * out[3..5] weight-gradient kernel */
+extern "C" int dvd_conv2d_cluster_info(int* out) {
+  static bool a1[16] = {}, a2[16] = {};
+  if (int e = per_device_attr((const void*)conv2d_tc_kernel, kSmem, a1)) return e;
+  if (int e = per_device_attr((const void*)conv_wgrad_kernel, kWgSmem, a2)) return e;
+  const int cs[3] = {1, 2, 4};
+  for (int i = 0; i < 3; ++i) {
+    out[i] = cs[i] * max_clusters(conv2d_tc_kernel, kThreads, kSmem, cs[i]);
+    out[3 + i] = cs[i] * max_clusters(conv_wgrad_kernel, 192, kWgSmem, cs[i]);
+  }
   return 0;
 }

@@ -34,7 +34,16 @@ def test_eval_forward_matches_oracle():
         P = geometry.unproject(d, R1, t1, Kinv)
         sf = sf_mlp.sf_multi_step(P, batch['time_stamp_1'], float(pair['time_step']), 1, sf_mlp.layers_from_state_dict(sd_m))
     assert rel_err(torch.from_numpy(out['depth']), d) < 1e-3
-    assert rel_err(torch.from_numpy(out['sf_1_2']), sf) < 1e-3
+    # the scene flow is the MLP evaluated on the un-projected points of the TF32 depth map: its periodic embedding (frequencies
+    # up to 17) amplifies the 1.5e-4 depth difference; on the oracle's own depth map the kernel chain agrees to 1e-3
+    assert rel_err(torch.from_numpy(out['sf_1_2']), sf) < 1e-2
+    from dvd_b200 import ops
+    with torch.no_grad():
+        Pg = ops.unproject_fwd(d.cuda().contiguous(), ops.pack_poses(pair['K'], pair['K_inv'], pair['R_1_T'], pair['R_1_T'],
+                                                                    pair['t_1'], pair['t_1']).cuda(), 1)
+        sfg = ops.mlp_chain_fwd(model.net_sceneflow.packed(opt.sf_mag_div), Pg, batch['time_stamp_1'].cuda().contiguous(),
+                                float(pair['time_step']), 1, 1, want_steps=False)['acc']
+    assert rel_err(sfg, sf) < 1e-3
     log = model._vali_on_batch(1, 0, batch)
     ref = torch.nn.functional.mse_loss(1 / d, torch.full_like(d, 1 / 5.0)).item()
     assert abs(log['loss'] - ref) <= 1e-3 * abs(ref) and log['size'] == 1
