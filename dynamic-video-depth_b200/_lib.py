@@ -85,9 +85,6 @@ SIGNATURES = {
                        ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), _P, _I, _I, _I, _P],
     'dvd_head_fwd': [_P, _P, _P, _P, ctypes.c_long, _P],
     'dvd_head_bwd': [_P, _P, _P, _P, _P, _P, _P, ctypes.c_long, _I, _I, _P],
-    'dvd_conv_pack_weight': [_P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _I, _I, _I, _I, _P],
-    'dvd_conv_nhwc_wgrad': [_P, _P, _P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _I, _I, _I, _I, _I, _I, _P],
-    'dvd_conv_nhwc_fwd': [_P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
 }
 _RESTYPES = {'dvd_last_error': ctypes.c_char_p, 'dvd_mlp_packed_weights_bytes': ctypes.c_size_t,
              'dvd_mlp_save_bytes_per_eval': ctypes.c_size_t, 'dvd_mlp_dy_bytes': ctypes.c_size_t}

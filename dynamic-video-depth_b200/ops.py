@@ -442,110 +442,6 @@ def bn_act(x, bn, res=None, relu=True):
     return BnAct.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, relu)
 
 
-_CONV_DEBUG = bool(int(__import__('os').environ.get('DVD_CONV_DEBUG', '0')))
-
-
-def pack_conv_weight(weight, dgrad=False):
-    """weight [Cout,Cin,k,k] (any strides: contiguous or channels-last storage) -> the tap-major, TF32-rounded image
-    dvd_conv_nhwc_fwd streams with TMA: [k*k][Cout][Cin]; dgrad=True gives the data-gradient image
-    [k*k rotated by 180 degrees][Cin][Cout] (the adjoint of a stride-1 'same' convolution is a convolution with it)."""
-    co, ci, kh, kw = weight.shape
-    if kh != kw or weight.dtype != torch.float32 or not weight.is_cuda:
-        raise ValueError('pack_conv_weight needs a square float32 CUDA kernel')
-    out = torch.empty((kh * kw, ci, co) if dgrad else (kh * kw, co, ci), dtype=torch.float32, device=weight.device)
-    st = weight.stride()
-    lib = _lib.load()
-    LAUNCHES['n'] += 1
-    _lib.check(lib.dvd_conv_pack_weight(_ptr(weight), st[0], st[1], st[2], st[3], _ptr(out), co, ci, kh, int(bool(dgrad)),
-                                        _stream()), 'dvd_conv_pack_weight')
-    return out
-
-
-def conv_nhwc_fwd(x, w_tkc, ksize, bias=None, bn=None, res=None, relu=False):
-    """tcgen05 TF32 convolution (stride 1, dense, 'same' padding for ksize 3) on a channels-last tensor x [N,C,H,W]
-    (memory NHWC): y = act(BN(conv(x, w) + bias) + res); `bn` = (gamma, beta, running_mean, running_var, eps) of an
-    eval-mode BatchNorm2d or None. Returns a channels-last [N,Cout,H,W] tensor. Forward only (no autograd graph)."""
-    x = _as_cl(x)
-    if x.dtype != torch.float32 or not x.is_cuda:
-        raise ValueError('conv_nhwc_fwd needs float32 CUDA tensors')
-    N, C, H, W = x.shape
-    taps, cout, cin = w_tkc.shape
-    if taps != ksize * ksize or cin != C:
-        raise ValueError('packed weight %s does not match ksize=%d, Cin=%d' % (tuple(w_tkc.shape), ksize, C))
-    r = _as_cl(res) if res is not None else None
-    g, b, m, v, eps = bn if bn is not None else (None, None, None, None, 0.0)
-    y = torch.empty((N, cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-    lib = _lib.load()
-    LAUNCHES['n'] += 1
-    if _CONV_DEBUG:
-        torch.cuda.synchronize()
-        print('conv_nhwc_fwd N=%d H=%d W=%d Cin=%d Cout=%d k=%d bias=%s bn=%s res=%s relu=%s' % (
-            N, H, W, C, cout, ksize, bias is not None, bn is not None, res is not None, relu), flush=True)
-    _lib.check(lib.dvd_conv_nhwc_fwd(_ptr(x), _ptr(w_tkc), _ptr(bias), _ptr(g), _ptr(b), _ptr(m), _ptr(v), float(eps), _ptr(r),
-                                     _ptr(y), N, H, W, C, cout, int(ksize), int(bool(relu)), _stream()), 'dvd_conv_nhwc_fwd')
-    return y
-
-
-def conv_nhwc_wgrad(x, gy, dweight):
-    """dweight[co,ci,ky,kx] += sum_px gy[px,co] * x[px + (ky-1,kx-1), ci] on the tcgen05 TF32 kernel (stride 1, dense,
-    'same' padding). x, gy: channels-last [N,C,H,W]; dweight: fp32 CUDA tensor [Cout,Cin,k,k] with any strides
-    (accumulated in place - zero it first for a plain gradient)."""
-    x, gy = _as_cl(x), _as_cl(gy)
-    N, C, H, W = x.shape
-    co, ci, kh, kw = dweight.shape
-    if gy.shape != (N, co, H, W) or ci != C or kh != kw:
-        raise ValueError('shape mismatch: x %s gy %s dweight %s' % (tuple(x.shape), tuple(gy.shape), tuple(dweight.shape)))
-    st = dweight.stride()
-    lib = _lib.load()
-    LAUNCHES['n'] += 1
-    _lib.check(lib.dvd_conv_nhwc_wgrad(_ptr(x), _ptr(gy), _ptr(dweight), st[0], st[1], st[2], st[3], N, H, W, C, co, kh,
-                                       _stream()), 'dvd_conv_nhwc_wgrad')
-    return dweight
-
-
-def conv_tc_supported(cin, cout, k):
-    """Shapes all three tcgen05 convolution kernels accept (forward, data gradient = forward kernel with the roles of the
-    channel counts swapped, weight gradient)."""
-    fwd = cin % 32 == 0 and cout % 16 == 0 and (cout <= 256 or cout % 256 == 0)
-    dgrad = cout % 32 == 0 and cin % 16 == 0 and (cin <= 256 or cin % 256 == 0)
-    wgrad = cout % 128 == 0 and cin % 32 == 0 and (cin <= 256 or cin % 256 == 0)
-    return k in (1, 3) and fwd and dgrad and wgrad
-
-
-class ConvTc(torch.autograd.Function):
-    """Dense stride-1 'same' convolution (+ bias) with all three passes on the tcgen05 TF32 kernels of csrc/conv_tc.cu.
-    STAGED FOR ROUND 2: the three kernels are parity-tested one by one (tests/test_conv_gpu.py); this Function and its use
-    in the MiDaS mirror (DVD_CONV_TC_TRAIN=1) were written after the round's GPU budget was spent and have not run on a
-    GPU yet - tests/test_zz_conv_train_gpu.py is their (equally opt-in) test.
-    forward(x channels-last [N,Cin,H,W], weight [Cout,Cin,k,k], bias|None) -> y channels-last [N,Cout,H,W]"""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias):
-        x = _as_cl(x)
-        y = conv_nhwc_fwd(x, pack_conv_weight(weight), weight.shape[2], bias)
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, weight = ctx.saved_tensors
-        gy = _as_cl(gy)
-        k = weight.shape[2]
-        gx = conv_nhwc_fwd(gy, pack_conv_weight(weight, dgrad=True), k) if ctx.needs_input_grad[0] else None
-        gw = None
-        if ctx.needs_input_grad[1]:
-            # like BnAct: accumulate straight into an existing .grad (the flat gradient buffer, zeroed once per step) and
-            # hand autograd None for it; otherwise return a fresh gradient with the weight's own strides
-            if weight.grad is not None and weight.grad.dtype == torch.float32 and weight.grad.is_cuda:
-                conv_nhwc_wgrad(x, gy, weight.grad)
-            else:
-                gw = torch.zeros_like(weight)
-                conv_nhwc_wgrad(x, gy, gw)
-        gb = gy.sum(dim=(0, 2, 3)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return gx, gw, gb
-
-
 class Upsample2x(torch.autograd.Function):
     """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=...) on channels-last tensors."""
 

@@ -194,32 +194,6 @@ int dvd_upsample2x_fwd(const float* x, float* y, int N, int H, int W, int C, int
 int dvd_upsample2x_bwd(const float* g, float* gx, int N, int H, int W, int C, int align_corners, int round_out, void* stream);
 /* round_out = 1: results stored rounded to TF32 (round-to-nearest) - they feed a tensor-core convolution (see below) */
 
-/* D1 / D2 dense stride-1 convolutions (1x1, 3x3 "same") on tcgen05 tensor cores, NHWC fp32 tensors, TF32 operands, fp32
- * accumulation:  y = act(BN(conv(x, w) + bias) + res)   - replaces torch.nn.Conv2d (cuDNN) followed by eval-mode
- * BatchNorm2d, the residual add and ReLU (torchvision Bottleneck.forward; third_party/midas_blocks.py:28-39,53-68,121-168;
- * third_party/MiDaS.py:188-195). With the tap-flipped, transposed weight image it is also the data gradient.
- * x [N,H,W,Cin], w_tkc [ksize*ksize][Cout][Cin] (tap-major packing of weight[co,ci,ky,kx]); bias [Cout] or NULL; eval-mode
- * BatchNorm as (gamma, beta, running_mean, running_var, eps), all four pointers or all NULL; res [N,H,W,Cout] or NULL;
- * y [N,H,W,Cout].  Needs Cin % 32 == 0, Cout % 16 == 0 (Cout <= 256 or a multiple of 256): returns -2 otherwise so that
- * the caller keeps such layers (stem, grouped / strided convolutions, the 32->1 head) on its library path.               */
-int dvd_conv_nhwc_fwd(const float* x, const float* w_tkc, const float* bias, const float* bn_gamma, const float* bn_beta,
-                      const float* bn_mean, const float* bn_var, float bn_eps, const float* res, float* y,
-                      int N, int H, int W, int Cin, int Cout, int ksize, int relu, void* stream);
-
-/* weight[co,ci,ky,kx] with the given element strides (contiguous or channels-last parameter storage) -> the tap-major
- * image w_tkc of dvd_conv_nhwc_fwd, operands rounded to TF32 with round-to-nearest (what cuDNN does; the tensor core
- * itself would truncate). dgrad = 1 packs the data-gradient image [k*k rotated][Cin][Cout].                              */
-int dvd_conv_pack_weight(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx,
-                         float* w_tkc, int Cout, int Cin, int ksize, int dgrad, void* stream);
-
-/* weight gradient of the same convolutions: dweight[co,ci,ky,kx] += sum_px gy[px,co] * x[px + (ky-1,kx-1), ci]  (ACCUMULATES
- * with fp32 reductions into the caller's gradient buffer, addressed with the given element strides - contiguous or
- * channels-last parameter storage). x [N,H,W,Cin], gy [N,H,W,Cout] NHWC fp32, TF32 tensor cores. Needs Cout % 128 == 0 and
- * Cin % 32 == 0 (Cin <= 256 or a multiple of 256): returns -2 otherwise. Replaces cuDNN's convolution_backward weight path.  */
-int dvd_conv_nhwc_wgrad(const float* x, const float* gy, float* dweight, long stride_co, long stride_ci, long stride_ky,
-                        long stride_kx, int N, int H, int W, int Cin, int Cout, int ksize, void* stream);
-
-
 /* ---- D1 / D1' depth-net convolutions, general form (csrc/conv2d_tc.cu) -------------------------------------------------
  * One implicit-GEMM tcgen05 (TF32) kernel family for every convolution class of MiDaS / ResNeXt101-32x8d
  * (third_party/MiDaS.py:188-246, third_party/midas_blocks.py:48-68,102-168, torchvision Bottleneck): dense and grouped,

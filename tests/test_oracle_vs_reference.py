@@ -85,3 +85,42 @@ def test_mlp_oracle_matches_reference_module(ns):
     t = torch.full((1, 1, 9, 11), 0.4)
     with torch.no_grad():
         assert rel_err(sf_mlp.mlp_forward(p, t, sf_mlp.layers_from_state_dict(net.state_dict())), net(p, t)) < 1e-5
+
+
+def test_reference_written_checkpoint_loads(tmp_path):
+    """A checkpoint written by the REFERENCE's own `NetInterface.save_state_dict` (models/netinterface.py:528-536) after one of its
+    optimisation steps loads into the dvd_b200 Model: same net keys / values, and its two torch.optim.Adam state dicts map onto the
+    flat Adam buffers (exp_avg, exp_avg_sq, step) and come back out identical. Hourglass variant (21 MB instead of 420 MB)."""
+    from dvd_b200 import synthetic
+    from dvd_b200.flat import FlatAdam, FlatParams
+    from dvd_b200.models import get_model
+    opt = ref_harness.default_opt(midas=False, lr=1e-4)
+    ref_model, _ = ref_harness.build_reference_model(opt, seed=0)
+    batch = synthetic.make_batch([(3, 5)], H=32, W=48, seed=1, smooth_flow=True)
+    ref_model._train_on_batch(6, 0, {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()})
+    f = str(tmp_path / 'ref.pt')
+    ref_model.save_state_dict(f, save_optimizer=True, additional_values={'epoch': 6})
+    ref_sd = torch.load(f, map_location='cpu', weights_only=False)
+    import dvd_b200.models.scene_flow_motion_field as mine_mod
+    mine_mod.depth_pretrain_path = None       # (with the reference on sys.path its configs/__init__.py names a file that is not here)
+    mine = get_model('scene_flow_motion_field')(synthetic.default_opt(midas=False, lr=1e-4), None)
+    extra = mine.load_state_dict(f)
+    assert extra.get('epoch') == 6
+    for net, rsd in zip(mine._nets, ref_sd['nets']):
+        msd = net.state_dict()
+        assert list(msd) == list(rsd)
+        for k in rsd:
+            assert torch.equal(msd[k], rsd[k]), k
+    # optimiser state: reference dict -> flat buffers -> dict (FlatParams / FlatAdam hold plain tensors: works on the CPU too)
+    for net, osd in zip(mine._nets, ref_sd['optimizers']):
+        adam = FlatAdam(FlatParams(net), 1e-4, (0.5, 0.9))
+        adam.load_state_dict(osd)
+        back = adam.state_dict()
+        # torch.optim.Adam keeps state only for parameters that ever received a gradient (the hourglass has unused layers);
+        # the flat optimiser writes (all-zero) moments for the others as well
+        assert set(osd['state']) <= set(back['state'])
+        for i in set(back['state']) - set(osd['state']):
+            assert float(back['state'][i]['exp_avg'].abs().max()) == 0.0 and float(back['state'][i]['exp_avg_sq'].abs().max()) == 0.0
+        for i, st in osd['state'].items():
+            assert int(float(back['state'][i]['step'])) == int(float(st['step']))
+            assert torch.equal(back['state'][i]['exp_avg'], st['exp_avg']) and torch.equal(back['state'][i]['exp_avg_sq'], st['exp_avg_sq'])
