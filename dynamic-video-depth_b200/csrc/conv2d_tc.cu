@@ -33,12 +33,12 @@ namespace {
 using namespace tc;
 
 constexpr int kStages = 4;
-constexpr int kThreads = 192;               // TMA producer, MMA issuer, 4 epilogue warps
+constexpr int kThreads = 320;               // TMA producer, MMA issuer, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kABytes = 128 * 128;          // 128 pixels x 32 fp32 channels
 constexpr int kMaxNT = 256;
 constexpr int kStageBytes = kABytes + kMaxNT * 128;
 constexpr int kStgBytes = 32 * 128;         // staging: 32 pixel rows x 32 channels
-constexpr int kOffStg = kStages * kStageBytes;              // 4 warps x 2 buffers
+constexpr int kOffStg = kStages * kStageBytes;              // 8 warps x 1 buffer
 constexpr int kOffAff = kOffStg + 8 * kStgBytes;            // scale[256] | shift[256]
 constexpr int kOffBar = kOffAff + 2 * kMaxNT * 4;
 constexpr size_t kSmem = kOffBar + 256;
@@ -154,10 +154,11 @@ __device__ __forceinline__ Tile decode_tile(const ConvParams& P, int ct, int m_t
   return t;
 }
 
-// acc -> mask * relu(acc * scale + shift + res + res2), optionally rounded to TF32; NC consecutive channels of one pixel
+// acc -> mask * relu(acc * scale + shift + res + res2), optionally rounded to TF32; NC consecutive channels of one pixel.
+// res / mask arrive in registers (the epilogue loads them one block ahead: they are what it would otherwise wait for).
 template <int NC>
-__device__ __forceinline__ void epilogue_math(const ConvParams& P, uint32_t (&r)[NC], const float* aff, const float* rrow,
-                                              const float* r2row, const float* mrow) {
+__device__ __forceinline__ void epilogue_math(const ConvParams& P, uint32_t (&r)[NC], const float* aff, const float4* resv,
+                                              const float* r2row, const float4* maskv) {
 #pragma unroll
   for (int j = 0; j < NC; j += 4) {
     float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
@@ -165,8 +166,8 @@ __device__ __forceinline__ void epilogue_math(const ConvParams& P, uint32_t (&r)
       const float4 sc = *reinterpret_cast<const float4*>(aff + j), sh = *reinterpret_cast<const float4*>(aff + kMaxNT + j);
       v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
     }
-    if (rrow) {
-      const float4 a = *reinterpret_cast<const float4*>(rrow + j);
+    if (resv) {
+      const float4 a = resv[j / 4];
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
     }
     if (r2row) {
@@ -174,13 +175,18 @@ __device__ __forceinline__ void epilogue_math(const ConvParams& P, uint32_t (&r)
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
     }
     if (P.d.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    if (mrow) {
-      const float4 m = *reinterpret_cast<const float4*>(mrow + j);
+    if (maskv) {
+      const float4 m = maskv[j / 4];
       v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
     }
     if (P.d.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
     r[j] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y); r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
   }
+}
+template <int NV>
+__device__ __forceinline__ void load_row(const float* row, float4 (&v)[NV]) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(row) + j);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     tmem_alloc(tmem_holder, 512);
   } else if (warp == 0 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)P.csize); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -277,13 +283,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ===== epilogue: one pixel (accumulator row) per thread =====
+    // ===== epilogue: one pixel (accumulator row) per thread; two warps per TMEM lane quarter take alternate channel blocks =====
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int hsel = (warp - 2) >> 2;            // 0 / 1: even / odd channel blocks
+    const int et = threadIdx.x - 64;             // 0..255 among the epilogue threads
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    uint8_t* stg = smem + kOffStg + (size_t)q * 2 * kStgBytes;
+    uint8_t* sb = smem + kOffStg + (size_t)(warp - 2) * kStgBytes;
     const bool has_aff = P.gamma != nullptr || P.bias != nullptr;
-    uint32_t lt = 0, nstore = 0;
+    uint32_t lt = 0;
     for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
       const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
       const Tile T = decode_tile(P, tile, m_tiles, mgroups, crank);
@@ -295,39 +303,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
       const float* r2row = (P.res2 && valid) ? P.res2 + off : nullptr;
       const float* mrow = (P.mask && valid) ? P.mask + off : nullptr;
       float* yrow = P.y + off;
-      if (has_aff) {
-        // fold BatchNorm / bias of this tile's channels once: y = acc * scale + shift
-        asm volatile("bar.sync 2, 128;" ::: "memory");      // previous tile's readers are done
-        for (int i = row; i < P.NT; i += 128) {
-          const int c = T.n0 + i;
-          float sc = 1.f, sh = 0.f;
-          if (P.gamma) {
-            sc = __ldg(P.gamma + c) * rsqrtf(__ldg(P.var + c) + P.d.bn_eps);
-            sh = __ldg(P.beta + c) - __ldg(P.mean + c) * sc;
-          }
-          if (P.bias) sh = fmaf(__ldg(P.bias + c), sc, sh);
-          aff_mem[i] = sc;
-          aff_mem[kMaxNT + i] = sh;
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-      }
-      mbar_wait(&acc_full[buf], aph);
-      tc_fence_after();
-      const uint32_t d = tmem + buf * (uint32_t)kMaxNT + lane_base;
       if (P.tma_store) {
+        // residual / mask of this warp's first block: in flight while the MMAs of the tile are still running
+        float4 resv[8], maskv[8];
+        if (rrow) load_row<8>(rrow + hsel * 32, resv);
+        if (mrow) load_row<8>(mrow + hsel * 32, maskv);
+        if (has_aff) {
+          // fold BatchNorm / bias of this tile's channels once: y = acc * scale + shift
+          asm volatile("bar.sync 2, 256;" ::: "memory");      // previous tile's readers are done
+          for (int i = et; i < P.NT; i += 256) {
+            const int c = T.n0 + i;
+            float sc = 1.f, sh = 0.f;
+            if (P.gamma) {
+              sc = __ldg(P.gamma + c) * rsqrtf(__ldg(P.var + c) + P.d.bn_eps);
+              sh = __ldg(P.beta + c) - __ldg(P.mean + c) * sc;
+            }
+            if (P.bias) sh = fmaf(__ldg(P.bias + c), sc, sh);
+            aff_mem[i] = sc;
+            aff_mem[kMaxNT + i] = sh;
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+        mbar_wait(&acc_full[buf], aph);
+        tc_fence_after();
+        const uint32_t d = tmem + buf * (uint32_t)kMaxNT + lane_base;
         const int bh0 = T.h0 + (q * 32) / P.TW, bw0 = T.w0 + (q * 32) % P.TW;
-        for (int c0 = 0; c0 < P.NT; c0 += 32, ++nstore) {
+        for (int c0 = hsel * 32; c0 < P.NT; c0 += 64) {
           uint32_t r[32];
           tmem_ld32(d + c0, r);
           tmem_ld_wait();
-          if (c0 + 32 >= P.NT) {                  // accumulator fully read: hand it back to the MMA warp
+          if (c0 + 64 >= P.NT) {                  // this warp has read its share of the accumulator
             tc_fence_before();
             mbar_arrive(&acc_empty[buf]);
           }
-          epilogue_math<32>(P, r, has_aff ? aff_mem + c0 : nullptr, rrow ? rrow + c0 : nullptr, r2row ? r2row + c0 : nullptr,
-                            mrow ? mrow + c0 : nullptr);
-          uint8_t* sb = stg + (nstore & 1u) * kStgBytes;
-          if (lane == 0) bulk_wait_read<1>();      // the store that last read this buffer has drained it
+          epilogue_math<32>(P, r, has_aff ? aff_mem + c0 : nullptr, rrow ? resv : nullptr, r2row ? r2row + c0 : nullptr,
+                            mrow ? maskv : nullptr);
+          if (c0 + 64 < P.NT) {                   // next block's residual / mask: in flight during the staging / store below
+            if (rrow) load_row<8>(rrow + c0 + 64, resv);
+            if (mrow) load_row<8>(mrow + c0 + 64, maskv);
+          }
+          if (lane == 0) bulk_wait_read<0>();      // the store that last read this warp's staging buffer has drained it
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -339,13 +354,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
             bulk_commit();
           }
         }
+        if (hsel * 32 >= P.NT) {                  // NT = 32: the odd warps have no block, but owe their arrival
+          tc_fence_before();
+          mbar_arrive(&acc_empty[buf]);
+        }
       } else {
-        for (int c0 = 0; c0 < P.NT; c0 += 16) {
+        if (has_aff) {
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          for (int i = et; i < P.NT; i += 256) {
+            const int c = T.n0 + i;
+            float sc = 1.f, sh = 0.f;
+            if (P.gamma) {
+              sc = __ldg(P.gamma + c) * rsqrtf(__ldg(P.var + c) + P.d.bn_eps);
+              sh = __ldg(P.beta + c) - __ldg(P.mean + c) * sc;
+            }
+            if (P.bias) sh = fmaf(__ldg(P.bias + c), sc, sh);
+            aff_mem[i] = sc;
+            aff_mem[kMaxNT + i] = sh;
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+        mbar_wait(&acc_full[buf], aph);
+        tc_fence_after();
+        const uint32_t d = tmem + buf * (uint32_t)kMaxNT + lane_base;
+        for (int c0 = hsel * 16; c0 < P.NT; c0 += 32) {
           uint32_t r[16];
           tmem_ld16(d + c0, r);
+          float4 rcur[4], mcur[4];
+          if (rrow) load_row<4>(rrow + c0, rcur);
+          if (mrow) load_row<4>(mrow + c0, mcur);
           tmem_ld_wait();
-          epilogue_math<16>(P, r, has_aff ? aff_mem + c0 : nullptr, rrow ? rrow + c0 : nullptr, r2row ? r2row + c0 : nullptr,
-                            mrow ? mrow + c0 : nullptr);
+          epilogue_math<16>(P, r, has_aff ? aff_mem + c0 : nullptr, rrow ? rcur : nullptr, r2row ? r2row + c0 : nullptr,
+                            mrow ? mcur : nullptr);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)

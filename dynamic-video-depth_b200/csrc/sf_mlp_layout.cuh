@@ -46,6 +46,12 @@ __host__ __device__ inline int rows_dy(int l) { return l == 5 ? 16 : kWidth; }
 //          write 512 contiguous bytes per 16-byte store;
 //   false: MN-major SWIZZLE_128B (mn128_offset) — each thread writes 16-byte pieces of its own 128-byte rows.
 constexpr bool kActInterleave = true;
+// Planes of the SAVED activations X_l / dY_l (the operands of the weight-gradient GEMM only): 1 = the bf16 `hi` plane alone.
+// dW = sum over >= 1e5 pixels of dY * X: the round-to-nearest bf16 errors of the two operands (2^-9 relative, zero mean,
+// independent from pixel to pixel) average out in that sum - the error of dW is ~1e-3 * sqrt(sum t^2) against |sum t|, i.e.
+// ~1e-6 of the largest entry at 384x224 - while the saved bytes, the HBM-bound weight-gradient kernel's traffic and its MMA
+// count halve / drop 3x. The forward chain and the data gradient keep the full (hi, lo) split in tensor memory.
+constexpr int kSavePlanes = 1;
 // bytes of one 64-pixel block of an activation / dY array with `rows` channels
 __host__ __device__ inline uint32_t blk_bytes(int rows) {
   return kActInterleave ? (uint32_t)((rows + 7) / 8) * 1024u : (uint32_t)((rows + 63) / 64) * 8192u;
@@ -76,7 +82,7 @@ inline MlpLayout make_layout(const dvd_mlp_cfg& c, long npx) {
   o = 0;
   for (int l = 0; l < kLayers; ++l) {
     L.xs_off[l] = o;
-    o += (size_t)2 * L.nq * blk_bytes(rows_x(L, l));
+    o += (size_t)kSavePlanes * L.nq * blk_bytes(rows_x(L, l));
   }
   L.mask_off = o;
   o += (size_t)5 * L.ntiles * kTileM * 32;  // 5 layers x 256 bits per pixel
@@ -84,7 +90,7 @@ inline MlpLayout make_layout(const dvd_mlp_cfg& c, long npx) {
   o = 0;
   for (int l = 0; l < kLayers; ++l) {
     L.dy_off[l] = o;
-    o += (size_t)2 * L.nq * blk_bytes(rows_dy(l));
+    o += (size_t)kSavePlanes * L.nq * blk_bytes(rows_dy(l));
   }
   L.dy_total = (o + 255) & ~(size_t)255;
   return L;

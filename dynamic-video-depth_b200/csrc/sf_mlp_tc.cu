@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
             if (SAVE) {
               const uint32_t o = act_offset(2 * w, kq);
               *reinterpret_cast<uint32_t*>(x0_hi + o) = hi;
-              *reinterpret_cast<uint32_t*>(x0_lo + o) = lo;
+              if (kSavePlanes == 2) *reinterpret_cast<uint32_t*>(x0_lo + o) = lo;
             }
           };
           if (E::kPaired) {
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
               for (int h = 0; h < 4; ++h) {
                 const uint32_t o = act_offset(c0 + 8 * h, kq);
                 st_global_v4(x_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
-                st_global_v4(x_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
+                if (kSavePlanes == 2) st_global_v4(x_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
               }
               maskp[cb] = mb;
             }
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
         for (int h = 0; h < 2; ++h) {
           const uint32_t o = act_offset(8 * h, kq);
           st_global_v4(y_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
-          st_global_v4(y_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
+          if (kSavePlanes == 2) st_global_v4(y_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
         }
       }
       tmem_st_wait();
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
           for (int h = 0; h < 4; ++h) {
             const uint32_t o = act_offset(c0 + 8 * h, kq);
             st_global_v4(y_hi + o, hi[4 * h], hi[4 * h + 1], hi[4 * h + 2], hi[4 * h + 3]);
-            st_global_v4(y_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
+            if (kSavePlanes == 2) st_global_v4(y_lo + o, lo[4 * h], lo[4 * h + 1], lo[4 * h + 2], lo[4 * h + 3]);
           }
         }
         tmem_st_wait();
@@ -668,8 +668,8 @@ struct WgradParams {
   WgradJob job[12];
   long nq;
 };
-constexpr int kWgStages = 2;
-constexpr uint32_t kWgStageBytes = 2 * 16384 + 2 * 32768;
+constexpr int kWgStages = kSavePlanes == 2 ? 2 : 4;
+constexpr uint32_t kWgStageBytes = kSavePlanes * (16384 + 32768);      // per plane: A 128 ch x 64 px, B up to 256 ch x 64 px (bf16)
 constexpr size_t kWgradSmemBytes = 1024 + (size_t)kWgStages * kWgStageBytes + 8192 + 256;
 
 __global__ void __launch_bounds__(kThreadsWgrad, 1) mlp_wgrad_kernel(const __grid_constant__ WgradParams P) {
@@ -712,12 +712,14 @@ __global__ void __launch_bounds__(kThreadsWgrad, 1) mlp_wgrad_kernel(const __gri
       for (long qq = q0; qq < q1; ++qq, ++it) {
         const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], 2 * a_bytes + 2 * b_bytes);
+        mbar_arrive_expect_tx(&full[s], kSavePlanes * (a_bytes + b_bytes));
         uint8_t* d = stage[s];
         bulk_g2s(d, J.a_hi + (size_t)qq * J.a_blk + J.a_row_off, a_bytes, &full[s]);
-        bulk_g2s(d + 16384, J.a_lo + (size_t)qq * J.a_blk + J.a_row_off, a_bytes, &full[s]);
-        bulk_g2s(d + 32768, J.b_hi + (size_t)qq * J.b_blk, b_bytes, &full[s]);
-        bulk_g2s(d + 65536, J.b_lo + (size_t)qq * J.b_blk, b_bytes, &full[s]);
+        bulk_g2s(d + 16384, J.b_hi + (size_t)qq * J.b_blk, b_bytes, &full[s]);
+        if (kSavePlanes == 2) {
+          bulk_g2s(d + 49152, J.a_lo + (size_t)qq * J.a_blk + J.a_row_off, a_bytes, &full[s]);
+          bulk_g2s(d + 65536, J.b_lo + (size_t)qq * J.b_blk, b_bytes, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -729,17 +731,18 @@ __global__ void __launch_bounds__(kThreadsWgrad, 1) mlp_wgrad_kernel(const __gri
         const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t sa_hi = smem_u32(stage[s]), sa_lo = sa_hi + 16384, sb_hi = sa_hi + 32768, sb_lo = sa_hi + 65536;
+        const uint32_t sa_hi = smem_u32(stage[s]), sb_hi = sa_hi + 16384, sa_lo = sa_hi + 49152, sb_lo = sa_hi + 65536;
         for (int ks = 0; ks < 4; ++ks) {   // 16 pixels (K rows of 128 B) per MMA
-          const uint64_t ah = act_desc(sa_hi, ks), al = act_desc(sa_lo, ks);
-          const uint64_t bh = act_desc(sb_hi, ks), bl = act_desc(sb_lo, ks);
+          const uint64_t ah = act_desc(sa_hi, ks), bh = act_desc(sb_hi, ks);
           umma_ss(tmem + 0, ah, bh, idesc, accum);
-          umma_ss(tmem + 0, al, bh, idesc, 1);
-          umma_ss(tmem + 0, ah, bl, idesc, 1);
+          if (kSavePlanes == 2) {
+            umma_ss(tmem + 0, act_desc(sa_lo, ks), bh, idesc, 1);
+            umma_ss(tmem + 0, ah, act_desc(sb_lo, ks), idesc, 1);
+          }
           if (J.bias_out) {
             const uint64_t od = act_desc(so, ks);
             umma_ss(tmem + 256, ah, od, idesc_b, accum);
-            umma_ss(tmem + 256, al, od, idesc_b, 1);
+            if (kSavePlanes == 2) umma_ss(tmem + 256, act_desc(sa_lo, ks), od, idesc_b, 1);
           }
           accum = 1;
         }
