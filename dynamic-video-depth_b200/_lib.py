@@ -71,9 +71,9 @@ SIGNATURES = {
     'dvd_upsample2x_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'dvd_upsample2x_bwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'dvd_conv2d_nhwc': [ctypes.POINTER(ConvDesc)] + [_P] * 11 + [_P],
-    'dvd_conv2d_pack': [_P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _I, _I, _I, _I, _I, _I, _P, _P, _F, _P],
+    'dvd_conv2d_pack': [_P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _P],
     'dvd_conv2d_wgrad': [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long,
-                         _I, _I, _P, _P, _P, _P],
+                         _I, _I, _P, _P, _P, _P, _P, _P],
     'dvd_conv2d_cluster_info': [ctypes.POINTER(ctypes.c_int)],
     'dvd_round_tf32': [_P, _P, ctypes.c_long, _P],
     'dvd_relu_bwd_colsum': [_P, _P, _P, _P, _P, _P, _F, _P, ctypes.c_long, _I, _I, _P],

@@ -104,25 +104,27 @@ def conv2d_launch(desc, x, w_img, y, bias=None, bn=None, res=None, res2=None, ma
     return y
 
 
-def pack_weight(weight, groups=1, mode=0, bn=None, out=None):
-    """weight [Cout, Cin/groups, k, k] (any strides) -> TF32-rounded image (see dvd_conv2d_pack). mode 0 forward, 1 data
-    gradient (rows = in-channels; scaled by the eval-BatchNorm factor of `bn` = (gamma, var, eps) when given)."""
+def pack_weight(weight, groups=1, bn=None, out_fwd=None, out_bwd=None, want_fwd=True, want_bwd=True):
+    """weight [Cout, Cin/groups, k, k] (any strides) -> TF32-rounded images (see dvd_conv2d_pack), both from one launch:
+    forward [k*k][Cout][cols] and data gradient [k*k][Cin][cols] (scaled by the eval-BatchNorm factor of `bn` = (gamma, var, eps)).
+    Returns (fwd, bwd); an image that is not wanted is None."""
     co, cil, kh, kw = weight.shape
     ci = cil * groups
     kblock = GROUP_BLOCK if groups > 1 else 0
-    rows = ci if mode else co
-    cols = kblock if kblock else (co if mode else ci)
-    if out is None:
-        out = torch.empty(kh * kw, rows, cols, dtype=torch.float32, device=weight.device)
+    if want_fwd and out_fwd is None:
+        out_fwd = torch.empty(kh * kw, co, kblock if kblock else ci, dtype=torch.float32, device=weight.device)
+    if want_bwd and out_bwd is None:
+        out_bwd = torch.empty(kh * kw, ci, kblock if kblock else co, dtype=torch.float32, device=weight.device)
     st = weight.stride()
     g, v, eps = bn if bn is not None else (None, None, 0.0)
     LAUNCHES['n'] += 1
-    _lib.check(_lib.load().dvd_conv2d_pack(_ptr(weight), st[0], st[1], st[2], st[3], _ptr(out), co, ci, kh, groups, kblock, int(mode),
-                                           _ptr(g), _ptr(v), float(eps), _stream()), 'dvd_conv2d_pack')
-    return out
+    _lib.check(_lib.load().dvd_conv2d_pack(_ptr(weight), st[0], st[1], st[2], st[3], _ptr(out_fwd if want_fwd else None),
+                                           _ptr(out_bwd if want_bwd else None), co, ci, kh, groups, kblock, _ptr(g), _ptr(v), float(eps),
+                                           _stream()), 'dvd_conv2d_pack')
+    return (out_fwd if want_fwd else None), (out_bwd if want_bwd else None)
 
 
-def wgrad_launch(desc, x, gy, dweight, ksize, groups=1, weight=None, bn=None, dgamma=None, flops=0.0):
+def wgrad_launch(desc, x, gy, dweight, ksize, groups=1, weight=None, bn=None, dgamma=None, flops=0.0, colsum=None, bn_mean=None):
     st = dweight.stride()
     if weight is not None and weight.stride() != st:
         raise ValueError('parameter and gradient must share their strides')
@@ -130,8 +132,8 @@ def wgrad_launch(desc, x, gy, dweight, ksize, groups=1, weight=None, bn=None, dg
     LAUNCHES['n'] += 1
     ev = _prof('wgrad', flops, desc)
     _lib.check(_lib.load().dvd_conv2d_wgrad(ctypes.byref(desc), _ptr(x), _ptr(gy), _ptr(dweight), _ptr(weight), st[0], st[1], st[2],
-                                            st[3], int(ksize), int(groups), _ptr(g), _ptr(v), _ptr(dgamma), _stream()),
-               'dvd_conv2d_wgrad')
+                                            st[3], int(ksize), int(groups), _ptr(g), _ptr(v), _ptr(dgamma), _ptr(colsum), _ptr(bn_mean),
+                                            _stream()), 'dvd_conv2d_wgrad')
     if ev is not None:
         ev.record()
 
@@ -261,10 +263,11 @@ class Conv:
 
     def pack(self, need_bwd=True):
         w = self.conv.weight.detach()
-        self.w_fwd = pack_weight(w, self.groups, 0, out=self.w_fwd)
+        bn = (self.bn.weight.detach(), self.bn.running_var, self.bn.eps) if self.bn is not None else None
+        f, b = pack_weight(w, self.groups, bn=bn, out_fwd=self.w_fwd, out_bwd=self.w_bwd, want_bwd=need_bwd)
+        self.w_fwd = f
         if need_bwd:
-            bn = (self.bn.weight.detach(), self.bn.running_var, self.bn.eps) if self.bn is not None else None
-            self.w_bwd = pack_weight(w, self.groups, 1, bn=bn, out=self.w_bwd)
+            self.w_bwd = b
 
     def flops(self, N, OH, OW):
         """algorithmic FLOPs of one pass (forward = data gradient = weight gradient) over N x OH x OW output pixels"""
@@ -307,21 +310,31 @@ class Conv:
                           flops=self.flops(N, OH, OW) * len(taps) / (self.k * self.k))
         return gx
 
-    # -- weight gradient (accumulates into conv.weight.grad; BatchNorm: gy un-scaled, dgamma gets the <W, dW> term) ----
-    def wgrad(self, x, gy):
+    # -- weight gradient (accumulates into conv.weight.grad; BatchNorm: gy un-scaled, dgamma gets the <W, dW> term). With
+    #    `sums` the same launch reduces gy over the pixels: conv-bias gradient, or BatchNorm beta + the mean term of gamma ------
+    def can_fuse_sums(self):
+        return self.groups > 1 or self.cout % 128 == 0
+
+    def wgrad(self, x, gy, sums=False):
         N, C, H, W = x.shape
         _, Co, OH, OW = gy.shape
         w = self.conv.weight
         d = make_desc(N, H, W, self.cin, OH, OW, self.cout, fwd_taps(self.k, self.pad), self.stride,
                       bn_eps=self.bn.eps if self.bn is not None else 0.0)
+        fuse = sums and self.can_fuse_sums() and (self.bn is not None or self.conv.bias is not None)
+        if sums and not fuse:
+            self.bias_or_bn_grad(gy)
         if self.bn is not None:
             wgrad_launch(d, x, gy, w.grad, self.k, self.groups, weight=w.detach(), bn=(self.bn.weight.detach(), self.bn.running_var),
-                         dgamma=self.bn.weight.grad, flops=self.flops(N, OH, OW))
+                         dgamma=self.bn.weight.grad, flops=self.flops(N, OH, OW), colsum=self.bn.bias.grad if fuse else None,
+                         bn_mean=self.bn.running_mean if fuse else None)
         else:
-            wgrad_launch(d, x, gy, w.grad, self.k, self.groups, flops=self.flops(N, OH, OW))
+            wgrad_launch(d, x, gy, w.grad, self.k, self.groups, flops=self.flops(N, OH, OW),
+                         colsum=self.conv.bias.grad if fuse else None)
 
     def bias_or_bn_grad(self, gm):
-        """per-channel sums of the masked gradient: conv bias gradient, or BatchNorm beta gradient + the mean term of gamma's."""
+        """per-channel sums of the masked gradient in a kernel of their own (layers whose weight-gradient launch cannot carry them):
+        conv bias gradient, or BatchNorm beta gradient + the mean term of gamma's."""
         if self.bn is not None:
             relu_bwd_colsum(gm, colsum=self.bn.bias.grad, bn=(self.bn.running_mean, self.bn.running_var, self.bn.eps),
                             dgamma=self.bn.weight.grad, round_out=False)

@@ -415,25 +415,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
 // t = ky * k + kx (never flipped: the tap table of the launch carries the offsets). Entries outside a channel's group are
 // zero (block-diagonal image of a grouped convolution). Values rounded to TF32 (RN).
 __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict__ w, long s_co, long s_ci, long s_ky, long s_kx,
-                                                        float* __restrict__ out, int Cout, int Cin, int k, int cpg, int kblock,
-                                                        int mode, const float* __restrict__ gamma, const float* __restrict__ var,
-                                                        float eps) {
-  const int rows = mode ? Cin : Cout;
-  const int cols = kblock ? kblock : (mode ? Cout : Cin);
-  const long n = (long)k * k * rows * cols;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cols);
-    const long q = i / cols;
-    const int r = (int)(q % rows), t = (int)(q / rows);
-    const int ky = t / k, kx = t - ky * k;
-    const int cabs = kblock ? (r / kblock) * kblock + c : c;     // absolute channel index of the column
-    const int co = mode ? cabs : r, ci = mode ? r : cabs;
-    float v = 0.f;
-    if (co / (Cout / (Cin / cpg)) == ci / cpg) {                 // same group (dense: one group)
-      v = w[co * s_co + (ci % cpg) * s_ci + ky * s_ky + kx * s_kx];
-      if (mode && gamma) v *= gamma[co] * rsqrtf(var[co] + eps);
+                                                        float* __restrict__ out_fwd, float* __restrict__ out_bwd, int Cout, int Cin,
+                                                        int k, int cpg, int kblock, const float* __restrict__ gamma,
+                                                        const float* __restrict__ var, float eps) {
+  // both images have k*k * C * cols elements when Cin == Cout or dense; they are walked with one index each
+  const int opg = Cout / (Cin / cpg);        // out-channels per group
+  for (int mode = 0; mode < 2; ++mode) {
+    float* out = mode ? out_bwd : out_fwd;
+    if (!out) continue;
+    const int rows = mode ? Cin : Cout;
+    const int cols = kblock ? kblock : (mode ? Cout : Cin);
+    const long n = (long)k * k * rows * cols;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+      const int c = (int)(i % cols);
+      const long q = i / cols;
+      const int r = (int)(q % rows), t = (int)(q / rows);
+      const int ky = t / k, kx = t - ky * k;
+      const int cabs = kblock ? (r / kblock) * kblock + c : c;     // absolute channel index of the column
+      const int co = mode ? cabs : r, ci = mode ? r : cabs;
+      float v = 0.f;
+      if (co / opg == ci / cpg) {                                  // same group (dense: one group)
+        v = w[co * s_co + (ci % cpg) * s_ci + ky * s_ky + kx * s_kx];
+        if (mode && gamma) v *= gamma[co] * rsqrtf(var[co] + eps);
+      }
+      out[i] = round_tf32(v);
     }
-    out[i] = round_tf32(v);
   }
 }
 
@@ -451,7 +457,9 @@ constexpr int kWgStages = 2;
 constexpr int kWgPx = 64;                         // pixels (K) per stage
 constexpr int kWgBox = kWgPx * 128;               // bytes of one {32 ch, 64 px} box
 constexpr int kWgStageBytes = (4 + 8) * kWgBox;   // M: 128 channels, N: up to 256 channels
-constexpr size_t kWgSmem = (size_t)kWgStages * kWgStageBytes + 256;
+constexpr int kWgOffOnes = kWgStages * kWgStageBytes;         // [64 px x 32] tile of 1.0: N operand of the column-sum MMA
+constexpr int kWgOffBar = kWgOffOnes + kWgBox;
+constexpr size_t kWgSmem = (size_t)kWgOffBar + 256;
 
 struct WgradParams {
   float* dw;
@@ -470,6 +478,8 @@ struct WgradParams {
   const float* var;
   float eps;
   float* dgamma;
+  float* colsum;                   // [Mch] += sum over pixels of the M operand (conv-bias / BatchNorm-beta gradient), or null
+  const float* mean;               // with colsum and dgamma: dgamma[m] -= mean[m] * rstd[m] * colsum[m]
   signed char dy[DVD_CONV_MAX_TAPS], dx[DVD_CONV_MAX_TAPS];
   unsigned char wt[DVD_CONV_MAX_TAPS];
 };
@@ -489,7 +499,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
                                                           const __grid_constant__ CUtensorMap mapN,
                                                           const __grid_constant__ WgradParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kWgStages * kWgStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgOffBar);
   uint64_t* full = bars;
   uint64_t* empty = bars + kWgStages;
   uint64_t* acc_full = bars + 2 * kWgStages;
@@ -499,8 +509,12 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
     printf("dvd_b200: conv_wgrad_kernel: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
+  if (P.colsum) {     // every element 1.0: the swizzle of the operand image does not matter
+    for (int i = threadIdx.x; i < kWgBox / 4; i += blockDim.x) reinterpret_cast<float*>(smem + kWgOffOnes)[i] = 1.0f;
+    fence_proxy_async_smem();
+  }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, 256);
+    tmem_alloc(tmem_holder, 512);
   } else if (warp == 0 && lane == 0) {
     for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)P.csize); }
     mbar_init(acc_full, 1);
@@ -524,6 +538,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   const int m0 = ((rem / n_n) * P.csize + crank) * 128;
   const int n0 = P.cpg ? m0 : (rem % n_n) * P.NT;
   const int dy = P.dy[t], dx = P.dx[t];
+  // the CTAs of the first tap and first N tile also reduce their M operand over the pixels (one extra N = 16 MMA per K step)
+  const bool do_colsum = P.colsum != nullptr && t == 0 && (P.cpg || rem % n_n == 0);
   const int px_tiles = P.N * P.tiles_h * P.tiles_w;
   const int per = (px_tiles + P.ksplit - 1) / P.ksplit;
   const int kt0 = part * per, kt1 = min(px_tiles, kt0 + per);
@@ -554,7 +570,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_mn(128, P.NT);
+      const uint32_t idesc = make_idesc_tf32_mn(128, P.NT), idesc1 = make_idesc_tf32_mn(128, 16);
+      const uint32_t so = smem_u32(smem + kWgOffOnes);
       uint32_t it = 0;
       for (int kt = kt0; kt < kt1; ++kt, ++it) {
         const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
@@ -562,9 +579,13 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * kWgStageBytes), sb = sa + 4 * kWgBox;
 #pragma unroll
-        for (int ks = 0; ks < kWgPx / 8; ++ks)
+        for (int ks = 0; ks < kWgPx / 8; ++ks) {
           umma_ss_tf32(tmem, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox), make_sdesc_mn_sw128_32b(sb + ks * 1024, kWgBox), idesc,
                        (it | ks) ? 1u : 0u);
+          if (do_colsum)
+            umma_ss_tf32(tmem + 256, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox), make_sdesc_mn_sw128_32b(so + ks * 1024, kWgBox),
+                         idesc1, (it | ks) ? 1u : 0u);
+        }
         if (P.csize > 1) umma_commit_mc(&empty[s], cmask);
         else umma_commit(&empty[s]);
       }
@@ -628,6 +649,14 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         }
       }
     }
+    if (do_colsum) {
+      uint32_t r1;
+      tmem_ld1(d + 256, r1);
+      tmem_ld_wait();
+      const float cs = __uint_as_float(r1);
+      atomicAdd(P.colsum + m, cs);
+      if (P.dgamma && P.mean) dot = fmaf(-__ldg(P.mean + m), cs, dot);      // d gamma = rstd * (<W, dW> - mean * sum gm)
+    }
     if (P.dgamma) atomicAdd(P.dgamma + m, dot * rstd);
   }
   tc_fence_before();
@@ -635,7 +664,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   if (P.csize > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -829,29 +858,29 @@ extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const 
   return 0;
 }
 
-extern "C" int dvd_conv2d_pack(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx, float* w_img,
-                               int Cout, int Cin, int ksize, int groups, int kblock, int mode, const float* bn_gamma,
+extern "C" int dvd_conv2d_pack(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx, float* w_fwd,
+                               float* w_bwd, int Cout, int Cin, int ksize, int groups, int kblock, const float* bn_gamma,
                                const float* bn_var, float bn_eps, void* stream) {
-  DVD_ARG_CHECK(weight && w_img, "null pointer");
+  DVD_ARG_CHECK(weight && (w_fwd || w_bwd), "null pointer");
   DVD_ARG_CHECK(Cout >= 1 && Cin >= 1 && ksize >= 1 && ksize <= 11 && groups >= 1 && Cin % groups == 0 && Cout % groups == 0,
                 "bad weight shape");
   DVD_ARG_CHECK((groups == 1) == (kblock == 0), "kblock must be set exactly for grouped convolutions");
   const int cpg = Cin / groups;
   if (kblock) DVD_ARG_CHECK(Cin == Cout && kblock % cpg == 0 && Cin % kblock == 0, "grouped: needs Cin == Cout and cpg | kblock | Cin");
   DVD_ARG_CHECK((bn_gamma != nullptr) == (bn_var != nullptr), "BatchNorm scale needs gamma and var");
-  const int rows = mode ? Cin : Cout, cols = kblock ? kblock : (mode ? Cout : Cin);
-  const long n = (long)ksize * ksize * rows * cols;
+  const long n = (long)ksize * ksize * (Cout > Cin ? Cout : Cin) * (kblock ? kblock : (Cout > Cin ? Cin : Cout));
   int blocks = (int)((n + 255) / 256);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  conv_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(weight, stride_co, stride_ci, stride_ky, stride_kx, w_img, Cout, Cin, ksize,
-                                                           cpg, kblock, mode, bn_gamma, bn_var, bn_eps);
+  conv_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(weight, stride_co, stride_ci, stride_ky, stride_kx, w_fwd, w_bwd, Cout, Cin,
+                                                           ksize, cpg, kblock, bn_gamma, bn_var, bn_eps);
   DVD_CUDA_LAUNCH_CHECK("conv_pack_kernel");
   return 0;
 }
 
 extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const float* gy, float* dweight, const float* weight,
                                 long stride_co, long stride_ci, long stride_ky, long stride_kx, int ksize, int groups,
-                                const float* bn_gamma, const float* bn_var, float* dgamma, void* stream) {
+                                const float* bn_gamma, const float* bn_var, float* dgamma, float* colsum, const float* bn_mean,
+                                void* stream) {
   DVD_ARG_CHECK(desc && x && gy && dweight, "null pointer");
   const dvd_conv_desc& d = *desc;
   DVD_ARG_CHECK(d.N >= 1 && d.H >= 1 && d.W >= 1 && d.OH >= 1 && d.OW >= 1, "bad shape");
@@ -862,7 +891,7 @@ extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const
   WgradParams P{};
   P.dw = dweight; P.w = dgamma ? weight : nullptr;
   P.N = d.N; P.OH = d.OH; P.OW = d.OW; P.ntaps = d.ntaps; P.ksize = ksize; P.stride = d.stride;
-  P.gamma = bn_gamma; P.var = bn_var; P.eps = d.bn_eps; P.dgamma = dgamma;
+  P.gamma = bn_gamma; P.var = bn_var; P.eps = d.bn_eps; P.dgamma = dgamma; P.colsum = colsum; P.mean = bn_mean;
   for (int t = 0; t < d.ntaps; ++t) { P.dy[t] = d.dy[t]; P.dx[t] = d.dx[t]; P.wt[t] = d.wt[t]; }
   const int Cin = d.Cin, Cout = d.Cout;
   if (groups > 1) {
@@ -879,6 +908,7 @@ extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const
   } else if (Cin % 128 == 0 && Cout % 32 == 0 && (Cout <= 256 || Cout % 256 == 0) && !bn_gamma) {
     P.swap = 1; P.Mch = Cin; P.Nch = Cout; P.NT = Cout >= 256 ? 256 : Cout;
     P.s_m = stride_ci; P.s_n = stride_co;
+    DVD_ARG_CHECK(colsum == nullptr, "column sums are not available with swapped operands (Cout %% 128 != 0): use dvd_relu_bwd_colsum");
   } else {
     set_error("dvd_conv2d_wgrad: unsupported channel counts Cin=%d Cout=%d", Cin, Cout);
     return -2;

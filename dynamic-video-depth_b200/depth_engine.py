@@ -131,12 +131,10 @@ class MidasEngine:
         oc4 = self.oc4
         gm_h2 = co.head_bwd(S['h2'], oc4.weight, oc4.bias, g_depth, oc4.weight.grad, oc4.bias.grad, relu_mask=True)
         H1, W1 = S['h1'].shape[2:]
-        self.oc2.bias_or_bn_grad(gm_h2)
-        self.oc2.wgrad(S['h1'], gm_h2)
+        self.oc2.wgrad(S['h1'], gm_h2, sums=True)
         g_h1 = self.oc2.dgrad(gm_h2, H1, W1, round_out=False)
         g_h0 = co.upsample2x_bwd(g_h1, False)
-        self.oc0.bias_or_bn_grad(g_h0)
-        self.oc0.wgrad(S['p1'], g_h0)
+        self.oc0.wgrad(S['p1'], g_h0, sums=True)
         g_path = self.oc0.dgrad(g_h0, H1 // 2, W1 // 2, round_out=False)
         g_feat = [None] * 4
         for j, K in enumerate((0, 1, 2, 3)):      # refinenet1 .. refinenet4
@@ -145,20 +143,16 @@ class MidasEngine:
             g_o = co.upsample2x_bwd(g_path, True)
             Hk, Wk = g_o.shape[2:]
             rb = self.rcu_b[K]
-            rb.c2.bias_or_bn_grad(g_o)
-            rb.c2.wgrad(c1b, g_o)
+            rb.c2.wgrad(c1b, g_o, sums=True)
             g_c1b = rb.c2.dgrad(g_o, Hk, Wk, mask=c1b)
-            rb.c1.bias_or_bn_grad(g_c1b)
-            rb.c1.wgrad(t, g_c1b)
+            rb.c1.wgrad(t, g_c1b, sums=True)
             g_t = rb.c1.dgrad(g_c1b, Hk, Wk, res=g_o, mask=t)       # w.r.t. the pre-ReLU sum (t itself for refinenet4)
             if c1a is not None:
                 ra = self.rcu_a[K]
                 g_path = g_t                                         # the other fusion input: previous path
-                ra.c2.bias_or_bn_grad(g_t)
-                ra.c2.wgrad(c1a, g_t)
+                ra.c2.wgrad(c1a, g_t, sums=True)
                 g_c1a = ra.c2.dgrad(g_t, Hk, Wk, mask=c1a)
-                ra.c1.bias_or_bn_grad(g_c1a)
-                ra.c1.wgrad(lrK, g_c1a)
+                ra.c1.wgrad(lrK, g_c1a, sums=True)
                 g_lr = ra.c1.dgrad(g_c1a, Hk, Wk, res=g_t, mask=lrK)
             else:
                 g_lr = g_t
@@ -177,20 +171,16 @@ class MidasEngine:
                 x_in, y1, y2 = S['blocks'][bi]
                 Hi, Wi = x_in.shape[2:]
                 Ho, Wo = y2.shape[2:]
-                b.c3.bias_or_bn_grad(gm3)
-                b.c3.wgrad(y2, gm3)
+                b.c3.wgrad(y2, gm3, sums=True)
                 gm2 = b.c3.dgrad(gm3, Ho, Wo, mask=y2)
-                b.c2.bias_or_bn_grad(gm2)
-                b.c2.wgrad(y1, gm2)
+                b.c2.wgrad(y1, gm2, sums=True)
                 gm1 = b.c2.dgrad(gm2, Hi, Wi, mask=y1)
-                b.c1.bias_or_bn_grad(gm1)
-                b.c1.wgrad(x_in, gm1)
+                b.c1.wgrad(x_in, gm1, sums=True)
                 first = si == 0 and k == 0
                 # the block input is the previous block's ReLU output (mask) - and, at a stage boundary, also a decoder input
                 extra = g_feat[si - 1] if (k == 0 and si > 0) else None
                 if b.ds is not None:
-                    b.ds.bias_or_bn_grad(gm3)
-                    b.ds.wgrad(x_in, gm3)
+                    b.ds.wgrad(x_in, gm3, sums=True)
                     g_ds = b.ds.dgrad(gm3, Hi, Wi, round_out=False)
                     g_in = b.c1.dgrad(gm1, Hi, Wi, res=g_ds, res2=extra, mask=None if first else x_in, round_out=not first)
                 else:

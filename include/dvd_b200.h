@@ -225,21 +225,25 @@ int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const float* w_im
                     const float* mask, float* y, void* stream);
 
 /* weight[co, ci_local, ky, kx] (element strides given; groups of Cin/groups in-channels) -> TF32-rounded image
- *   mode 0: forward        [k*k][Cout][Cin or kblock]
- *   mode 1: data gradient  [k*k][Cin][Cout or kblock], multiplied by gamma*rsqrt(var+eps) of the out-channel when given
+ *   w_fwd: forward        [k*k][Cout][Cin or kblock]
+ *   w_bwd: data gradient  [k*k][Cin][Cout or kblock], multiplied by gamma*rsqrt(var+eps) of the out-channel when given
+ * (either may be NULL; both are written by one launch)
  * grouped convolutions (groups > 1) are packed block-diagonally with `kblock` channels per block (kblock = 0 when dense).   */
-int dvd_conv2d_pack(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx, float* w_img,
-                    int Cout, int Cin, int ksize, int groups, int kblock, int mode, const float* bn_gamma,
+int dvd_conv2d_pack(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx, float* w_fwd,
+                    float* w_bwd, int Cout, int Cin, int ksize, int groups, int kblock, const float* bn_gamma,
                     const float* bn_var, float bn_eps, void* stream);
 
 /* dweight[co, ci_local, ky, kx] += sc[co] * sum_px gy[px, co] * x[stride*px + (dy,dx)(tap), ci]   (fp32 reductions, any strides)
  * for the taps of `desc` (wt[t] = ky*ksize + kx). With an eval-mode BatchNorm behind the convolution, gy is the UN-scaled
  * masked gradient, sc = gamma*rsqrt(var+eps), and dgamma[co] += rsqrt(var+eps) * <weight[co], sum gy x> (weight = the
- * parameter tensor, same strides as dweight). Needs (128 | Cout and 32 | Cin) or (128 | Cin and 32 | Cout, no BatchNorm);
+ * parameter tensor, same strides as dweight). colsum (optional, not with swapped operands): colsum[co] += sum_px gy[px, co] - the
+ * conv-bias or BatchNorm-beta gradient - from one extra N = 16 MMA per K step against a ones operand; with bn_mean, dgamma also
+ * receives -mean * rsqrt(var+eps) * that sum. Needs (128 | Cout and 32 | Cin) or (128 | Cin and 32 | Cout, no BatchNorm);
  * grouped: Cin == Cout, 128 | C.                                                                                              */
 int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const float* gy, float* dweight, const float* weight,
                      long stride_co, long stride_ci, long stride_ky, long stride_kx, int ksize, int groups,
-                     const float* bn_gamma, const float* bn_var, float* dgamma, void* stream);
+                     const float* bn_gamma, const float* bn_var, float* dgamma, float* colsum, const float* bn_mean,
+                     void* stream);
 /* diagnostic: CTAs of the two tensor-core kernels that can be resident at once when launched in thread-block clusters of 1, 2, 4
  * (out[0..2] dvd_conv2d_nhwc, out[3..5] dvd_conv2d_wgrad): the library picks the cluster size that keeps the machine full.  */
 int dvd_conv2d_cluster_info(int* out6);

@@ -185,7 +185,8 @@ WGRAD_CASES = [
 @pytest.mark.parametrize('channels_last_weight', [False, True])
 @pytest.mark.parametrize('case', WGRAD_CASES)
 def test_conv_weight_gradient_matches_torch_fp64(case, channels_last_weight):
-    """dW = sc * sum gm x, dgamma += rstd * <W, sum gm x>; accumulating."""
+    """dW = sc * sum gm x; with `sums` the same launch also yields the per-channel sums of gm (one extra MMA against a ones operand):
+    d beta = sum gm and d gamma = rstd * (<W, sum gm x> - mean * sum gm); everything accumulates."""
     from dvd_b200 import conv_ops as co
     N, H, W, ci, co_, k, stride, groups, use_bn = case
     seed = 3000 * k + ci + co_ + H + 7 * stride + groups
@@ -199,7 +200,8 @@ def test_conv_weight_gradient_matches_torch_fp64(case, channels_last_weight):
     ref_dgamma = None
     if bn is not None:
         rstd = torch.rsqrt(bn.running_var.double() + bn.eps)
-        ref_dgamma = (ref * conv.weight.detach().double()).sum(dim=(1, 2, 3)) * rstd
+        ref_dbeta = gm.double().sum(dim=(0, 2, 3))
+        ref_dgamma = ((ref * conv.weight.detach().double()).sum(dim=(1, 2, 3)) - bn.running_mean.double() * ref_dbeta) * rstd
         ref = ref * (bn.weight.detach().double() * rstd).view(-1, 1, 1, 1)
     conv, bn = conv.cuda(), (bn.cuda() if bn is not None else None)
     if channels_last_weight and k > 1:
@@ -207,15 +209,39 @@ def test_conv_weight_gradient_matches_torch_fp64(case, channels_last_weight):
     conv.weight.grad = torch.zeros_like(conv.weight)
     if bn is not None:
         bn.weight.grad = torch.zeros_like(bn.weight)
+        bn.bias.grad = torch.zeros_like(bn.bias)
     c = co.Conv(conv, bn)
-    c.wgrad(cl(x), cl(gm))
+    c.wgrad(cl(x), cl(gm), sums=True)
     e = rel_err(conv.weight.grad, ref)
     assert e < TOL, e
     if bn is not None:
         e = rel_err(bn.weight.grad, ref_dgamma)
         assert e < 5e-5, e
-    c.wgrad(cl(x), cl(gm))          # accumulates
+        e = rel_err(bn.bias.grad, ref_dbeta)
+        assert e < 2e-5, e
+    c.wgrad(cl(x), cl(gm), sums=True)          # accumulates
     assert rel_err(conv.weight.grad, 2 * ref) < TOL
+    if bn is not None:
+        assert rel_err(bn.bias.grad, 2 * ref_dbeta) < 2e-5
+
+
+def test_conv_bias_gradient_rides_on_the_weight_gradient_launch():
+    from dvd_b200 import conv_ops as co
+    g = gen(77)
+    conv = make_conv(256, 256, 3, 1, 1, True, 78).cuda()
+    x = tf32(torch.randn(2, 256, 14, 24, generator=g))
+    gm = tf32(torch.randn(2, 256, 14, 24, generator=g))
+    conv.weight.grad, conv.bias.grad = torch.zeros_like(conv.weight), torch.zeros_like(conv.bias)
+    co.Conv(conv).wgrad(cl(x), cl(gm), sums=True)
+    assert rel_err(conv.bias.grad, gm.double().sum(dim=(0, 2, 3))) < 2e-5
+    # swapped operands (Cout = 32): the sums come from the stand-alone kernel
+    conv2 = make_conv(128, 32, 3, 1, 1, True, 79).cuda()
+    x2 = tf32(torch.randn(1, 128, 20, 28, generator=g))
+    gm2 = tf32(torch.randn(1, 32, 20, 28, generator=g))
+    conv2.weight.grad, conv2.bias.grad = torch.zeros_like(conv2.weight), torch.zeros_like(conv2.bias)
+    co.Conv(conv2).wgrad(cl(x2), cl(gm2), sums=True)
+    assert rel_err(conv2.bias.grad, gm2.double().sum(dim=(0, 2, 3))) < 2e-5
+    assert rel_err(conv2.weight.grad, torch.nn.grad.conv2d_weight(x2.double(), conv2.weight.shape, gm2.double(), padding=1)) < TOL
 
 
 def test_relu_bwd_colsum():

@@ -25,7 +25,7 @@ def test_eval_forward_matches_oracle():
     # per-frame batch of the reference's validation loader (datasets/davis_sequence.py:114-154)
     batch = {'img': pair['img_1'], 'R_1': pair['R_1'], 't_1': pair['t_1'], 'K_inv': pair['K_inv'],
              'time_stamp_1': pair['time_stamp_1'], 'time_step': pair['time_step'],
-             'depth_mvs': torch.full((1, 1, H, W), 5.0), 'pair_path': ['x']}
+             'depth_mvs': torch.full((1, 1, H, W), 8.0), 'pair_path': ['x']}
     model.eval()
     out = model.test_on_batch(0, batch)
     with torch.no_grad():
@@ -45,5 +45,5 @@ def test_eval_forward_matches_oracle():
                                 float(pair['time_step']), 1, 1, want_steps=False)['acc']
     assert rel_err(sfg, sf) < 1e-3
     log = model._vali_on_batch(1, 0, batch)
-    ref = torch.nn.functional.mse_loss(1 / d, torch.full_like(d, 1 / 5.0)).item()
+    ref = torch.nn.functional.mse_loss(1 / d, torch.full_like(d, 1 / 8.0)).item()   # (a target near the prediction would make the MSE ill-conditioned)
     assert abs(log['loss'] - ref) <= 1e-3 * abs(ref) and log['size'] == 1

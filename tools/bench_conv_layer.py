@@ -18,13 +18,16 @@ def main():
     bn = torch.nn.BatchNorm2d(co_).cuda().eval()
     conv.weight.grad = torch.zeros_like(conv.weight)
     bn.weight.grad = torch.zeros_like(bn.weight)
+    bn.bias.grad = torch.zeros_like(bn.bias)
+    if co_ % 128 and groups == 1:
+        bn = None        # swapped weight-gradient operands carry no BatchNorm
     c = co.Conv(conv, bn)
     c.pack()
     OH, OW = c.out_hw(H, W)
     x = co.round_tf32(torch.randn(N, ci, H, W, device='cuda').contiguous(memory_format=torch.channels_last))
     gy = co.round_tf32(torch.randn(N, co_, OH, OW, device='cuda').contiguous(memory_format=torch.channels_last))
     res = torch.randn(N, co_, OH, OW, device='cuda').contiguous(memory_format=torch.channels_last)
-    fn = {'fwd': lambda: c.fwd(x, res=res, relu=True), 'dgrad': lambda: c.dgrad(gy, H, W, mask=x), 'wgrad': lambda: c.wgrad(x, gy)}[kind]
+    fn = {'fwd': lambda: c.fwd(x, res=res, relu=True), 'dgrad': lambda: c.dgrad(gy, H, W, mask=x), 'wgrad': lambda: c.wgrad(x, gy, sums=True)}[kind]
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
