@@ -372,12 +372,15 @@ def roofline_depth_convs(model, batch, epoch, tflops_peak, peak_kind):
     import torch
     from dvd_b200 import conv_ops
     conv_ops.PROFILE = []
+    graph_flag = getattr(model.opt, 'cuda_graph', True)
+    model.opt.cuda_graph = False          # the probe brackets individual launches: run this one step eagerly
     try:
         model._train_on_batch(epoch, 0, batch)
         torch.cuda.synchronize()
         rec = conv_ops.PROFILE
     finally:
         conv_ops.PROFILE = None
+        model.opt.cuda_graph = graph_flag
     agg = {}
     for kind, flops, e0, e1, _info in rec:
         a = agg.setdefault(kind, [0.0, 0.0, 0])

@@ -61,6 +61,9 @@ struct ConvParams {
   int sbw, sbh;                   // per-warp store box: sbw x sbh = 32 pixels
   int csize;                      // thread-block cluster size (1, 2, 4): the CTAs of a cluster work on consecutive pixel tiles of
                                   // the same channel tile and share the weight stream (each loads NT/csize rows, multicast to all)
+  int pair;                       // csize == 2 as ONE tcgen05 CTA pair (cta_group::2): M = 256 pixels per MMA, each CTA keeps its own
+                                  // 128-pixel A tile and HALF of the weight tile in shared memory (the tensor core reads both halves),
+                                  // so the per-SM shared-memory traffic of the weight operand - the measured bound - halves
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -97,6 +100,51 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                "h"(mask)
                : "memory");
+}
+// address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// cta_group::2 TMA loads: data lands in THIS CTA's shared memory, the bytes are counted on the pair leader's mbarrier
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// D[tmem of both CTAs, 256 x N] (+)= A[128 rows in each CTA] * B[N/2 rows in each CTA]^T, issued by the pair leader
+__device__ __forceinline__ void umma_ss_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -208,10 +256,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     __trap();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, 512);
+    if (P.pair) tmem_alloc_2sm(tmem_holder, 512);
+    else tmem_alloc(tmem_holder, 512);
   } else if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)P.csize); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
+    // pair mode: one commit of the leader's MMA thread (multicast) frees a stage in both CTAs; the leader's accumulator is
+    // drained by the epilogue threads of BOTH CTAs
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], P.pair ? 1u : (uint32_t)P.csize); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], P.pair ? 512u : 256u); }
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -248,6 +299,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
             uint8_t* st = smem + (size_t)s * kStageBytes;
             mbar_wait(&empty[s], ph ^ 1u);            // every CTA of the cluster has drained this stage
+            if (P.pair) {
+              // both CTAs' bytes (own A tile + own half of the weight tile each) are counted on the leader's barrier
+              const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&full[s], 2u * ((uint32_t)kABytes + (uint32_t)wslice * 128u));
+              tma_load_4d_2sm(st, &mapA, kbase + kc * 32, ws + dx, hs + dy, T.img, lbar);
+              tma_load_3d_2sm(st + kABytes, &mapW, kc * 32, T.n0 + crank * wslice, wt, lbar);
+              continue;
+            }
             mbar_arrive_expect_tx(&full[s], stage_tx);
             tma_load_4d(st, &mapA, kbase + kc * 32, ws + dx, hs + dy, T.img, &full[s]);
             if (P.csize > 1)
@@ -259,9 +318,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, P.NT);
+    // ===== MMA issuer (pair mode: the leader CTA issues for both) =====
+    if (lane == 0 && !(P.pair && crank != 0)) {
+      const uint32_t idesc = make_idesc_tf32(P.pair ? 256 : 128, P.NT);
       uint32_t it = 0, lt = 0;
       for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
         const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
@@ -273,13 +332,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
+          if (P.pair) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss_tf32_2sm(d, make_sdesc_k_sw128(sa + ks * 32), make_sdesc_k_sw128(sb + ks * 32), idesc, (k | ks) ? 1u : 0u);
+            umma_commit_2sm_mc(&empty[s], 3);
+            continue;
+          }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_ss_tf32(d, make_sdesc_k_sw128(sa + ks * 32), make_sdesc_k_sw128(sb + ks * 32), idesc, (k | ks) ? 1u : 0u);
           if (P.csize > 1) umma_commit_mc(&empty[s], cmask);   // the stage also holds weight rows written by the peers
           else umma_commit(&empty[s]);
         }
-        umma_commit(&acc_full[buf]);
+        if (P.pair) umma_commit_2sm_mc(&acc_full[buf], 3);
+        else umma_commit(&acc_full[buf]);
       }
     }
   } else {
@@ -291,6 +358,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     uint8_t* sb = smem + kOffStg + (size_t)(warp - 2) * kStgBytes;
     const bool has_aff = P.gamma != nullptr || P.bias != nullptr;
+    // "this thread has read its part of accumulator `b`": in pair mode the arrival goes to the leader CTA's barrier
+    auto release_acc = [&](uint32_t b) {
+      tc_fence_before();
+      if (P.pair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[b]), 0));
+      else mbar_arrive(&acc_empty[b]);
+    };
     uint32_t lt = 0;
     for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
       const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
@@ -332,10 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
           uint32_t r[32];
           tmem_ld32(d + c0, r);
           tmem_ld_wait();
-          if (c0 + 64 >= P.NT) {                  // this warp has read its share of the accumulator
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
-          }
+          if (c0 + 64 >= P.NT) release_acc(buf);  // this warp has read its share of the accumulator
           epilogue_math<32>(P, r, has_aff ? aff_mem + c0 : nullptr, rrow ? resv : nullptr, r2row ? r2row + c0 : nullptr,
                             mrow ? maskv : nullptr);
           if (c0 + 64 < P.NT) {                   // next block's residual / mask: in flight during the staging / store below
@@ -354,10 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
             bulk_commit();
           }
         }
-        if (hsel * 32 >= P.NT) {                  // NT = 32: the odd warps have no block, but owe their arrival
-          tc_fence_before();
-          mbar_arrive(&acc_empty[buf]);
-        }
+        if (hsel * 32 >= P.NT) release_acc(buf);  // NT = 32: the odd warps have no block, but owe their arrival
       } else {
         if (has_aff) {
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -392,8 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
               *reinterpret_cast<uint4*>(yrow + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
           }
         }
-        tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        release_acc(buf);
       }
     }
     if (P.tma_store && lane == 0) bulk_wait_all();
@@ -403,7 +469,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
   if (P.csize > 1) cluster_sync_all();         // no CTA leaves while a peer may still multicast into it / signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    if (P.pair) tmem_dealloc_2sm(tmem, 512);
+    else tmem_dealloc(tmem, 512);
   }
 }
 
@@ -473,6 +540,8 @@ struct WgradParams {
   int ksplit;
   int csize;                       // cluster size: the CTAs of a cluster own consecutive 128-row M blocks of the same (tap, N tile,
                                    // pixel range) and share the N-operand stream (each loads every csize-th box, multicast)
+  int pair;                        // csize == 2 as one tcgen05 CTA pair: M = 256 rows per MMA, each CTA keeps HALF of the N operand
+                                   // (64 KB instead of 96 KB per 64-pixel stage: three stages instead of two)
   int cpg;                         // > 0: grouped (diagonal blocks, NT = 128)
   const float* gamma;              // eval BatchNorm of the out-channels (or null)
   const float* var;
@@ -500,23 +569,28 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
                                                           const __grid_constant__ WgradParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgOffBar);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kWgStages;
-  uint64_t* acc_full = bars + 2 * kWgStages;
+  uint64_t* full = bars;            // [<= 4]
+  uint64_t* empty = bars + 4;       // [<= 4]
+  uint64_t* acc_full = bars + 8;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("dvd_b200: conv_wgrad_kernel: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
+  const int nb = P.NT / 32;                                   // 32-channel boxes of the N tile
+  const int nb_own = P.pair ? nb / 2 : nb;                    // ... resident in this CTA's shared memory
+  const int nstages = P.pair ? 3 : kWgStages;
+  const uint32_t stage_bytes = (uint32_t)(4 + nb_own) * kWgBox <= 65536u && P.pair ? 65536u : (uint32_t)kWgStageBytes;
   if (P.colsum) {     // every element 1.0: the swizzle of the operand image does not matter
     for (int i = threadIdx.x; i < kWgBox / 4; i += blockDim.x) reinterpret_cast<float*>(smem + kWgOffOnes)[i] = 1.0f;
     fence_proxy_async_smem();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, 512);
+    if (P.pair) tmem_alloc_2sm(tmem_holder, 512);
+    else tmem_alloc(tmem_holder, 512);
   } else if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)P.csize); }
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], P.pair ? 1u : (uint32_t)P.csize); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -543,21 +617,29 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   const int px_tiles = P.N * P.tiles_h * P.tiles_w;
   const int per = (px_tiles + P.ksplit - 1) / P.ksplit;
   const int kt0 = part * per, kt1 = min(px_tiles, kt0 + per);
-  const int nb = P.NT / 32;
   const uint32_t stage_tx = (uint32_t)(4 + nb) * kWgBox;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
       for (int kt = kt0; kt < kt1; ++kt, ++it) {
-        const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
+        const uint32_t s = it % nstages, ph = (it / nstages) & 1u;
         const int img = kt / (P.tiles_h * P.tiles_w), r = kt - img * (P.tiles_h * P.tiles_w);
         const int h0 = (r / P.tiles_w) * P.TH, w0 = (r % P.tiles_w) * P.TW;
         // gy is sampled on the plain pixel grid, x at stride * pixel + tap offset
         const int gw = w0, gh = h0, xw = w0 * P.stride + dx, xh = h0 * P.stride + dy;
         const int mw = P.swap ? xw : gw, mh = P.swap ? xh : gh, nw = P.swap ? gw : xw, nh = P.swap ? gh : xh;
-        uint8_t* st = smem + (size_t)s * kWgStageBytes;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_wait(&empty[s], ph ^ 1u);
+        if (P.pair) {
+          // own 128 M rows + own half of the N tile; both CTAs' bytes are counted on the leader's barrier
+          const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0);
+          if (crank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)(4 + nb_own) * kWgBox);
+          for (int j = 0; j < 4; ++j) tma_load_4d_2sm(st + j * kWgBox, &mapM, m0 + 32 * j, mw, mh, img, lbar);
+          for (int j = 0; j < nb_own; ++j)
+            tma_load_4d_2sm(st + (4 + j) * kWgBox, &mapN, n0 + 32 * (crank * nb_own + j), nw, nh, img, lbar);
+          continue;
+        }
         mbar_arrive_expect_tx(&full[s], stage_tx);
         for (int j = 0; j < 4; ++j) tma_load_4d(st + j * kWgBox, &mapM, m0 + 32 * j, mw, mh, img, &full[s]);
         if (P.csize > 1) {
@@ -569,15 +651,28 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_mn(128, P.NT), idesc1 = make_idesc_tf32_mn(128, 16);
+    if (lane == 0 && !(P.pair && crank != 0)) {
+      const int Mi = P.pair ? 256 : 128;
+      const uint32_t idesc = make_idesc_tf32_mn(Mi, P.NT), idesc1 = make_idesc_tf32_mn(Mi, 16);
       const uint32_t so = smem_u32(smem + kWgOffOnes);
       uint32_t it = 0;
       for (int kt = kt0; kt < kt1; ++kt, ++it) {
-        const uint32_t s = it % kWgStages, ph = (it / kWgStages) & 1u;
+        const uint32_t s = it % nstages, ph = (it / nstages) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * kWgStageBytes), sb = sa + 4 * kWgBox;
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + 4 * kWgBox;
+        if (P.pair) {
+#pragma unroll
+          for (int ks = 0; ks < kWgPx / 8; ++ks) {
+            umma_ss_tf32_2sm(tmem, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox), make_sdesc_mn_sw128_32b(sb + ks * 1024, kWgBox), idesc,
+                             (it | ks) ? 1u : 0u);
+            if (do_colsum)
+              umma_ss_tf32_2sm(tmem + 256, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox),
+                               make_sdesc_mn_sw128_32b(so + ks * 1024, kWgBox), idesc1, (it | ks) ? 1u : 0u);
+          }
+          umma_commit_2sm_mc(&empty[s], 3);
+          continue;
+        }
 #pragma unroll
         for (int ks = 0; ks < kWgPx / 8; ++ks) {
           umma_ss_tf32(tmem, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox), make_sdesc_mn_sw128_32b(sb + ks * 1024, kWgBox), idesc,
@@ -589,7 +684,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         if (P.csize > 1) umma_commit_mc(&empty[s], cmask);
         else umma_commit(&empty[s]);
       }
-      umma_commit(acc_full);
+      if (P.pair) umma_commit_2sm_mc(acc_full, 3);
+      else umma_commit(acc_full);
     }
   } else if (kt1 > kt0) {
     // epilogue: accumulator row = M channel, columns = N channels of this tile
@@ -664,7 +760,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   if (P.csize > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    if (P.pair) tmem_dealloc_2sm(tmem, 512);
+    else tmem_dealloc(tmem, 512);
   }
 }
 
@@ -831,6 +928,12 @@ extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const 
     const int v = atoi(ev);
     if ((v == 1 || v == 2 || v == 4) && (P.NT / v) % 8 == 0) P.csize = v;
   }
+  // dense layers with at least two pixel tiles run as tcgen05 CTA pairs (cta_group::2); DVD_CONV_PAIR=0 falls back to multicast
+  P.pair = 0;
+  if (P.csize == 2 && d.kblock == 0 && P.NT % 32 == 0) {
+    const char* ev = getenv("DVD_CONV_PAIR");
+    P.pair = (ev && atoi(ev) == 0) ? 0 : 1;
+  }
   CUtensorMap mapA, mapW, mapY;
   if (int e = make_nhwc_map(&mapA, x, inN, inH, inW, d.Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   {
@@ -942,6 +1045,11 @@ extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const
       const int v = atoi(ev);
       if ((v == 1 || v == 2 || v == 4) && n_m % v == 0 && nb % v == 0) P.csize = v;
     }
+  }
+  P.pair = 0;
+  if (P.csize == 2 && (P.NT / 32) % 2 == 0) {
+    const char* ev = getenv("DVD_WGRAD_PAIR");
+    P.pair = (ev && atoi(ev) == 0) ? 0 : 1;
   }
   // split-K so that all CTAs are resident in ONE wave (a second, nearly empty wave would double the time)
   const int resident = P.csize * max_clusters(conv_wgrad_kernel, 192, kWgSmem, P.csize);

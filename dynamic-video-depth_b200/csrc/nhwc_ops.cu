@@ -154,9 +154,10 @@ __global__ void __launch_bounds__(kElemThreads) upsample2x_bwd_kernel(const floa
     const int ix = (int)(p % W); p /= W;
     const int iy = (int)(p % H);
     const int n = (int)(p / H);
-    // candidate output rows / columns: src in (iy-1, iy+1)  =>  dst within [2 iy - 4, 2 iy + 4] for both modes
-    const int oy_lo = max(0, 2 * iy - 4), oy_hi = min(OH - 1, 2 * iy + 4);
-    const int ox_lo = max(0, 2 * ix - 4), ox_hi = min(OW - 1, 2 * ix + 4);
+    // candidate output rows / columns: src in (iy-1, iy+1). align_corners=False: src = dst/2 - 1/4 => dst in [2iy-1, 2iy+2];
+    // align_corners=True: src = dst*(H-1)/(2H-1) => dst < 2(iy+1)(1 + 1/(2H-2)) <= 2iy+3 inside the image: [2iy-2, 2iy+3] covers both
+    const int oy_lo = max(0, 2 * iy - 2), oy_hi = min(OH - 1, 2 * iy + 3);
+    const int ox_lo = max(0, 2 * ix - 2), ox_hi = min(OW - 1, 2 * ix + 3);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* gb = g + (size_t)n * OH * OW * c4 + c;
     for (int oy = oy_lo; oy <= oy_hi; ++oy) {

@@ -23,7 +23,7 @@ def _digest(model):
     return out
 
 
-def _worker(rank, world, port, same_shard, q):
+def _worker(rank, world, port, same_shard, midas, q):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from dvd_b200 import synthetic
@@ -32,9 +32,9 @@ def _worker(rank, world, port, same_shard, q):
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     torch.backends.cudnn.allow_tf32 = False
-    opt = synthetic.default_opt(midas=False, lr=1e-4, multiprocess_distributed=True, global_rank=rank)
+    opt = synthetic.default_opt(midas=midas, lr=1e-4, multiprocess_distributed=True, global_rank=rank)
     model = get_model('scene_flow_motion_field')(opt, None)
-    synthetic.seed_net_(model.net_depth, 10 + rank)       # ranks start different: the broadcast must fix that
+    synthetic.seed_net_(model.net_depth, 10 + rank, 2000.0 if midas else None)       # ranks start different: the broadcast must fix that
     synthetic.seed_net_(model.net_sceneflow, 20 + rank)
     model.to(torch.device('cuda', rank))
     model.sync_parameters(0)
@@ -45,15 +45,15 @@ def _worker(rank, world, port, same_shard, q):
     dist.destroy_process_group()
 
 
-def _single(q):
+def _single(midas, q):
     sys.path.insert(0, ROOT)
     from dvd_b200 import synthetic
     from dvd_b200.models import get_model
     torch.cuda.set_device(0)
     torch.backends.cudnn.allow_tf32 = False
-    opt = synthetic.default_opt(midas=False, lr=1e-4)
+    opt = synthetic.default_opt(midas=midas, lr=1e-4)
     model = get_model('scene_flow_motion_field')(opt, None)
-    synthetic.seed_net_(model.net_depth, 10)
+    synthetic.seed_net_(model.net_depth, 10, 2000.0 if midas else None)
     synthetic.seed_net_(model.net_sceneflow, 20)
     model.to(torch.device('cuda', 0))
     batch = synthetic.make_batch([(10, 12)], H=64, W=96, seed=3, smooth_flow=True)
@@ -64,7 +64,7 @@ def _single(q):
 def _run(target, n, args):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=target, args=(r, *args, q) if n > 1 else (q,)) for r in range(n)]
+    procs = [ctx.Process(target=target, args=(r, *args, q) if n > 1 else (*args, q)) for r in range(n)]
     for p in procs:
         p.start()
     out = [q.get(timeout=600) for _ in procs]
@@ -75,10 +75,12 @@ def _run(target, n, args):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-def test_two_rank_step_equals_single_gpu_step_on_identical_shards():
-    port = 29700 + os.getpid() % 200
-    two = _run(_worker, 2, (2, port, True))
-    one = _run(_single, 1, ())[0]
+@pytest.mark.parametrize('midas', [False, True])
+def test_two_rank_step_equals_single_gpu_step_on_identical_shards(midas):
+    """midas=True: the tcgen05 depth engine with channels-last flat buffers and the bucketed, backward-overlapped all-reduce."""
+    port = 29700 + os.getpid() % 200 + (7 if midas else 0)
+    two = _run(_worker, 2, (2, port, True, midas))
+    one = _run(_single, 1, (midas,))[0]
     for r in two:
         assert abs(r[1] - one[1]) <= 1e-5 * abs(one[1])
         bad = []
@@ -86,14 +88,16 @@ def test_two_rank_step_equals_single_gpu_step_on_identical_shards():
             s2 = r[2][k][0]
             # Adam's first step moves every element by ~lr = 1e-4; elements whose gradient sign is ambiguous at fp32
             # rounding level may land 2e-4 apart: tolerate 0.5 % of them
-            if abs(s1 - s2) > 0.005 * n * 2e-4 + 1e-6 * a1:
+            # (MiDaS: fp32 atomics in the weight-gradient reductions make even two runs of one GPU differ in the last bits)
+            if abs(s1 - s2) > (0.02 if midas else 0.005) * n * 2e-4 + 1e-6 * a1:
                 bad.append((k, n, s1, s2))
         assert not bad, bad[:8]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-def test_ranks_stay_in_lockstep_on_different_shards():
-    port = 29900 + os.getpid() % 90
-    two = _run(_worker, 2, (2, port, False))
+@pytest.mark.parametrize('midas', [False, True])
+def test_ranks_stay_in_lockstep_on_different_shards(midas):
+    port = 29900 + os.getpid() % 90 + (5 if midas else 0)
+    two = _run(_worker, 2, (2, port, False, midas))
     assert two[0][1] != two[1][1]                    # different data, different losses
     assert two[0][2] == two[1][2]                    # bit-identical parameters on both ranks
