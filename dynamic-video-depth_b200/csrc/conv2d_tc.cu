@@ -237,6 +237,9 @@ __device__ __forceinline__ void load_row(const float* row, float4 (&v)[NV]) {
   for (int j = 0; j < NV; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(row) + j);
 }
 
+// kPair: compiled with the cta_group::2 instructions (such a kernel can only be launched in clusters of two: the plain variant
+// must not contain them)
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapW,
                                                                const __grid_constant__ CUtensorMap mapY,
@@ -256,13 +259,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     __trap();
   }
   if (warp == 1) {
-    if (P.pair) tmem_alloc_2sm(tmem_holder, 512);
+    if (kPair) tmem_alloc_2sm(tmem_holder, 512);
     else tmem_alloc(tmem_holder, 512);
   } else if (warp == 0 && lane == 0) {
     // pair mode: one commit of the leader's MMA thread (multicast) frees a stage in both CTAs; the leader's accumulator is
     // drained by the epilogue threads of BOTH CTAs
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], P.pair ? 1u : (uint32_t)P.csize); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], P.pair ? 512u : 256u); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kPair ? 1u : (uint32_t)P.csize); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPair ? 512u : 256u); }
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
             uint8_t* st = smem + (size_t)s * kStageBytes;
             mbar_wait(&empty[s], ph ^ 1u);            // every CTA of the cluster has drained this stage
-            if (P.pair) {
+            if (kPair) {
               // both CTAs' bytes (own A tile + own half of the weight tile each) are counted on the leader's barrier
               const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0);
               if (crank == 0) mbar_arrive_expect_tx(&full[s], 2u * ((uint32_t)kABytes + (uint32_t)wslice * 128u));
@@ -319,8 +322,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===== MMA issuer (pair mode: the leader CTA issues for both) =====
-    if (lane == 0 && !(P.pair && crank != 0)) {
-      const uint32_t idesc = make_idesc_tf32(P.pair ? 256 : 128, P.NT);
+    if (lane == 0 && !(kPair && crank != 0)) {
+      const uint32_t idesc = make_idesc_tf32(kPair ? 256 : 128, P.NT);
       uint32_t it = 0, lt = 0;
       for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
         const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
-          if (P.pair) {
+          if (kPair) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_ss_tf32_2sm(d, make_sdesc_k_sw128(sa + ks * 32), make_sdesc_k_sw128(sb + ks * 32), idesc, (k | ks) ? 1u : 0u);
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
           if (P.csize > 1) umma_commit_mc(&empty[s], cmask);   // the stage also holds weight rows written by the peers
           else umma_commit(&empty[s]);
         }
-        if (P.pair) umma_commit_2sm_mc(&acc_full[buf], 3);
+        if (kPair) umma_commit_2sm_mc(&acc_full[buf], 3);
         else umma_commit(&acc_full[buf]);
       }
     }
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     // "this thread has read its part of accumulator `b`": in pair mode the arrival goes to the leader CTA's barrier
     auto release_acc = [&](uint32_t b) {
       tc_fence_before();
-      if (P.pair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[b]), 0));
+      if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[b]), 0));
       else mbar_arrive(&acc_empty[b]);
     };
     uint32_t lt = 0;
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
   if (P.csize > 1) cluster_sync_all();         // no CTA leaves while a peer may still multicast into it / signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    if (P.pair) tmem_dealloc_2sm(tmem, 512);
+    if (kPair) tmem_dealloc_2sm(tmem, 512);
     else tmem_dealloc(tmem, 512);
   }
 }
@@ -564,6 +567,7 @@ __device__ __forceinline__ uint64_t make_sdesc_mn_sw128_32b(uint32_t smem_addr, 
 }
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) { return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
 
+template <bool kPair>
 __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constant__ CUtensorMap mapM,
                                                           const __grid_constant__ CUtensorMap mapN,
                                                           const __grid_constant__ WgradParams P) {
@@ -579,18 +583,18 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
     __trap();
   }
   const int nb = P.NT / 32;                                   // 32-channel boxes of the N tile
-  const int nb_own = P.pair ? nb / 2 : nb;                    // ... resident in this CTA's shared memory
-  const int nstages = P.pair ? 3 : kWgStages;
-  const uint32_t stage_bytes = (uint32_t)(4 + nb_own) * kWgBox <= 65536u && P.pair ? 65536u : (uint32_t)kWgStageBytes;
+  const int nb_own = kPair ? nb / 2 : nb;                    // ... resident in this CTA's shared memory
+  const int nstages = kPair ? 3 : kWgStages;
+  const uint32_t stage_bytes = (uint32_t)(4 + nb_own) * kWgBox <= 65536u && kPair ? 65536u : (uint32_t)kWgStageBytes;
   if (P.colsum) {     // every element 1.0: the swizzle of the operand image does not matter
     for (int i = threadIdx.x; i < kWgBox / 4; i += blockDim.x) reinterpret_cast<float*>(smem + kWgOffOnes)[i] = 1.0f;
     fence_proxy_async_smem();
   }
   if (warp == 1) {
-    if (P.pair) tmem_alloc_2sm(tmem_holder, 512);
+    if (kPair) tmem_alloc_2sm(tmem_holder, 512);
     else tmem_alloc(tmem_holder, 512);
   } else if (warp == 0 && lane == 0) {
-    for (int i = 0; i < nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], P.pair ? 1u : (uint32_t)P.csize); }
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kPair ? 1u : (uint32_t)P.csize); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -631,7 +635,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         const int mw = P.swap ? xw : gw, mh = P.swap ? xh : gh, nw = P.swap ? gw : xw, nh = P.swap ? gh : xh;
         uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_wait(&empty[s], ph ^ 1u);
-        if (P.pair) {
+        if (kPair) {
           // own 128 M rows + own half of the N tile; both CTAs' bytes are counted on the leader's barrier
           const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0);
           if (crank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)(4 + nb_own) * kWgBox);
@@ -651,8 +655,8 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && !(P.pair && crank != 0)) {
-      const int Mi = P.pair ? 256 : 128;
+    if (lane == 0 && !(kPair && crank != 0)) {
+      const int Mi = kPair ? 256 : 128;
       const uint32_t idesc = make_idesc_tf32_mn(Mi, P.NT), idesc1 = make_idesc_tf32_mn(Mi, 16);
       const uint32_t so = smem_u32(smem + kWgOffOnes);
       uint32_t it = 0;
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + 4 * kWgBox;
-        if (P.pair) {
+        if (kPair) {
 #pragma unroll
           for (int ks = 0; ks < kWgPx / 8; ++ks) {
             umma_ss_tf32_2sm(tmem, make_sdesc_mn_sw128_32b(sa + ks * 1024, kWgBox), make_sdesc_mn_sw128_32b(sb + ks * 1024, kWgBox), idesc,
@@ -684,7 +688,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         if (P.csize > 1) umma_commit_mc(&empty[s], cmask);
         else umma_commit(&empty[s]);
       }
-      if (P.pair) umma_commit_2sm_mc(acc_full, 3);
+      if (kPair) umma_commit_2sm_mc(acc_full, 3);
       else umma_commit(acc_full);
     }
   } else if (kt1 > kt0) {
@@ -760,7 +764,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   if (P.csize > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    if (P.pair) tmem_dealloc_2sm(tmem, 512);
+    if (kPair) tmem_dealloc_2sm(tmem, 512);
     else tmem_dealloc(tmem, 512);
   }
 }
@@ -914,13 +918,15 @@ extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const 
   P.sbw = P.TW < 32 ? P.TW : 32;
   P.sbh = 32 / P.sbw;
   static bool attr_done[16] = {};
-  if (int e = per_device_attr((const void*)conv2d_tc_kernel, kSmem, attr_done)) return e;
+  if (int e = per_device_attr((const void*)conv2d_tc_kernel<false>, kSmem, attr_done)) return e;
+  static bool attr_done_p[16] = {};
+  if (int e = per_device_attr((const void*)conv2d_tc_kernel<true>, kSmem, attr_done_p)) return e;
   // cluster size: the weight tile is fetched once per cluster (NT / csize rows per CTA, whole 8-row swizzle atoms)
   const long m_tiles_h = (long)d.N * P.tiles_w * P.tiles_h;
   P.csize = 1;
   {
     // clusters of 4 may leave SMs idle (a GPC whose SM count is not a multiple of 4): take 4 only when it keeps the machine full
-    const int sm4 = 4 * max_clusters(conv2d_tc_kernel, kThreads, kSmem, 4), sm2 = 2 * max_clusters(conv2d_tc_kernel, kThreads, kSmem, 2);
+    const int sm4 = 4 * max_clusters(conv2d_tc_kernel<false>, kThreads, kSmem, 4), sm2 = 2 * max_clusters(conv2d_tc_kernel<false>, kThreads, kSmem, 2);
     if (m_tiles_h >= 8 && P.NT % 32 == 0 && sm4 + 4 >= sm2) P.csize = 4;
     else if (m_tiles_h >= 2 && P.NT % 16 == 0) P.csize = 2;
   }
@@ -952,10 +958,12 @@ extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const 
     mapY = mapA;
   }
   const long ctiles = ((m_tiles_h + P.csize - 1) / P.csize) * (d.Cout / P.NT);      // cluster tiles
-  long nclusters = max_clusters(conv2d_tc_kernel, kThreads, kSmem, P.csize);
+  long nclusters = max_clusters(conv2d_tc_kernel<false>, kThreads, kSmem, P.csize);
   if (ctiles < nclusters) nclusters = ctiles;
-  if (int e = launch_clustered(conv2d_tc_kernel, (int)nclusters * P.csize, kThreads, kSmem, P.csize, (cudaStream_t)stream, mapA, mapW,
-                               mapY, P))
+  if (int e = P.pair ? launch_clustered(conv2d_tc_kernel<true>, (int)nclusters * P.csize, kThreads, kSmem, P.csize, (cudaStream_t)stream,
+                                        mapA, mapW, mapY, P)
+                     : launch_clustered(conv2d_tc_kernel<false>, (int)nclusters * P.csize, kThreads, kSmem, P.csize, (cudaStream_t)stream,
+                                        mapA, mapW, mapY, P))
     return e;
   DVD_CUDA_LAUNCH_CHECK("conv2d_tc_kernel");
   return 0;
@@ -1033,12 +1041,14 @@ extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const
   const int out_tiles = d.ntaps * (P.Mch / 128) * (P.cpg ? 1 : P.Nch / P.NT);
   const int px_tiles = N * P.tiles_h * P.tiles_w;
   static bool attr_done[16] = {};
-  if (int e = per_device_attr((const void*)conv_wgrad_kernel, kWgSmem, attr_done)) return e;
+  if (int e = per_device_attr((const void*)conv_wgrad_kernel<false>, kWgSmem, attr_done)) return e;
+  static bool attr_done_p[16] = {};
+  if (int e = per_device_attr((const void*)conv_wgrad_kernel<true>, kWgSmem, attr_done_p)) return e;
   // cluster over consecutive 128-row M blocks: they consume the same N-operand boxes
   P.csize = 1;
   if (!P.cpg) {
     const int n_m = P.Mch / 128, nb = P.NT / 32;
-    const int sm4 = 4 * max_clusters(conv_wgrad_kernel, 192, kWgSmem, 4), sm2 = 2 * max_clusters(conv_wgrad_kernel, 192, kWgSmem, 2);
+    const int sm4 = 4 * max_clusters(conv_wgrad_kernel<false>, 192, kWgSmem, 4), sm2 = 2 * max_clusters(conv_wgrad_kernel<false>, 192, kWgSmem, 2);
     if (n_m % 4 == 0 && nb % 4 == 0 && sm4 + 4 >= sm2) P.csize = 4;
     else if (n_m % 2 == 0 && nb % 2 == 0) P.csize = 2;
     if (const char* ev = getenv("DVD_WGRAD_CLUSTER")) {
@@ -1052,7 +1062,7 @@ extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const
     P.pair = (ev && atoi(ev) == 0) ? 0 : 1;
   }
   // split-K so that all CTAs are resident in ONE wave (a second, nearly empty wave would double the time)
-  const int resident = P.csize * max_clusters(conv_wgrad_kernel, 192, kWgSmem, P.csize);
+  const int resident = P.csize * max_clusters(conv_wgrad_kernel<false>, 192, kWgSmem, P.csize);
   int ksplit = resident / out_tiles;
   if (ksplit > px_tiles) ksplit = px_tiles;
   if (ksplit < 1) ksplit = 1;
@@ -1060,8 +1070,10 @@ extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const
   CUtensorMap mapG, mapX;
   if (int e = make_nhwc_map(&mapG, gy, N, OH, OW, Cout, P.TW, P.TH, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
   if (int e = make_nhwc_map(&mapX, x, N, H, W, Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return e;
-  if (int e = launch_clustered(conv_wgrad_kernel, out_tiles * ksplit, 192, kWgSmem, P.csize, (cudaStream_t)stream, P.swap ? mapX : mapG,
-                               P.swap ? mapG : mapX, P))
+  if (int e = P.pair ? launch_clustered(conv_wgrad_kernel<true>, out_tiles * ksplit, 192, kWgSmem, P.csize, (cudaStream_t)stream,
+                                        P.swap ? mapX : mapG, P.swap ? mapG : mapX, P)
+                     : launch_clustered(conv_wgrad_kernel<false>, out_tiles * ksplit, 192, kWgSmem, P.csize, (cudaStream_t)stream,
+                                        P.swap ? mapX : mapG, P.swap ? mapG : mapX, P))
     return e;
   DVD_CUDA_LAUNCH_CHECK("conv_wgrad_kernel");
   return 0;
@@ -1071,12 +1083,12 @@ extern "C" int dvd_conv2d_wgrad(const dvd_conv_desc* desc, const float* x, const
  * out[3..5] weight-gradient kernel */
 extern "C" int dvd_conv2d_cluster_info(int* out) {
   static bool a1[16] = {}, a2[16] = {};
-  if (int e = per_device_attr((const void*)conv2d_tc_kernel, kSmem, a1)) return e;
-  if (int e = per_device_attr((const void*)conv_wgrad_kernel, kWgSmem, a2)) return e;
+  if (int e = per_device_attr((const void*)conv2d_tc_kernel<false>, kSmem, a1)) return e;
+  if (int e = per_device_attr((const void*)conv_wgrad_kernel<false>, kWgSmem, a2)) return e;
   const int cs[3] = {1, 2, 4};
   for (int i = 0; i < 3; ++i) {
-    out[i] = cs[i] * max_clusters(conv2d_tc_kernel, kThreads, kSmem, cs[i]);
-    out[3 + i] = cs[i] * max_clusters(conv_wgrad_kernel, 192, kWgSmem, cs[i]);
+    out[i] = cs[i] * max_clusters(conv2d_tc_kernel<false>, kThreads, kSmem, cs[i]);
+    out[3 + i] = cs[i] * max_clusters(conv_wgrad_kernel<false>, 192, kWgSmem, cs[i]);
   }
   return 0;
 }
