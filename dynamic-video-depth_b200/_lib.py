@@ -32,6 +32,14 @@ class ConvDesc(ctypes.Structure):
                 ('wt', ctypes.c_ubyte * DVD_CONV_MAX_TAPS)]
 
 
+class PackItem(ctypes.Structure):
+    """struct dvd_pack_item (include/dvd_b200.h)."""
+    _fields_ = [('weight', ctypes.c_void_p), ('w_fwd', ctypes.c_void_p), ('w_bwd', ctypes.c_void_p), ('bn_gamma', ctypes.c_void_p),
+                ('bn_var', ctypes.c_void_p), ('s_co', ctypes.c_long), ('s_ci', ctypes.c_long), ('s_ky', ctypes.c_long),
+                ('s_kx', ctypes.c_long), ('blk0', ctypes.c_long), ('Cout', ctypes.c_int), ('Cin', ctypes.c_int),
+                ('ksize', ctypes.c_int), ('groups', ctypes.c_int), ('kblock', ctypes.c_int), ('bn_eps', ctypes.c_float)]
+
+
 class MlpCfg(ctypes.Structure):
     """struct dvd_mlp_cfg (include/dvd_b200.h)."""
     _fields_ = [('n_freq_xyz', ctypes.c_int), ('n_freq_t', ctypes.c_int), ('time_dependent', ctypes.c_int),
@@ -71,7 +79,11 @@ SIGNATURES = {
     'dvd_upsample2x_fwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'dvd_upsample2x_bwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'dvd_conv2d_nhwc': [ctypes.POINTER(ConvDesc)] + [_P] * 11 + [_P],
+    'dvd_conv2d_nhwc_ws': [ctypes.POINTER(ConvDesc)] + [_P] * 11 + [_P, ctypes.c_size_t, _P],
+    'dvd_conv2d_workspace_bytes': [],
     'dvd_conv2d_pack': [_P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _P],
+    'dvd_conv2d_pack_blocks': [_I, _I, _I, _I, _I],
+    'dvd_conv2d_pack_batch': [_P, _I, ctypes.c_long, _I, _P],
     'dvd_conv2d_wgrad': [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long,
                          _I, _I, _P, _P, _P, _P, _P, _P],
     'dvd_conv2d_cluster_info': [ctypes.POINTER(ctypes.c_int)],
@@ -86,7 +98,7 @@ SIGNATURES = {
     'dvd_head_fwd': [_P, _P, _P, _P, ctypes.c_long, _P],
     'dvd_head_bwd': [_P, _P, _P, _P, _P, _P, _P, ctypes.c_long, _I, _I, _P],
 }
-_RESTYPES = {'dvd_last_error': ctypes.c_char_p, 'dvd_mlp_packed_weights_bytes': ctypes.c_size_t,
+_RESTYPES = {'dvd_last_error': ctypes.c_char_p, 'dvd_conv2d_workspace_bytes': ctypes.c_size_t, 'dvd_conv2d_pack_blocks': ctypes.c_long, 'dvd_mlp_packed_weights_bytes': ctypes.c_size_t,
              'dvd_mlp_save_bytes_per_eval': ctypes.c_size_t, 'dvd_mlp_dy_bytes': ctypes.c_size_t}
 
 _lib = None

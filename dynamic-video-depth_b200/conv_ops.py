@@ -93,12 +93,32 @@ def make_desc(N, H, W, Cin, OH, OW, Cout, taps, stride=1, kblock=0, YH=None, YW=
 # ------------------------------------------------------------------------------------------------
 # raw launches
 
+_WORKSPACE = {}     # device index -> zero-initialised exchange area of the stream-K schedule (dvd_conv2d_nhwc_ws)
+
+
+def conv_workspace(device):
+    """The per-device exchange area of the convolution kernel's stream-K schedule. One area per device: all convolutions of a
+    process are issued on one stream at a time (the current stream, or the capture stream of the step graph); a caller that
+    runs convolutions concurrently on several streams must set DVD_CONV_STREAMK=0. Never allocated during a graph capture."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _WORKSPACE.get(idx)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        ws = torch.zeros(_lib.load().dvd_conv2d_workspace_bytes() // 4, dtype=torch.float32, device=torch.device('cuda', idx))
+        torch.cuda.current_stream(idx).synchronize()
+        _WORKSPACE[idx] = ws
+    return ws
+
+
 def conv2d_launch(desc, x, w_img, y, bias=None, bn=None, res=None, res2=None, mask=None, flops=0.0, kind='conv'):
     g, b, m, v = bn if bn is not None else (None, None, None, None)
     LAUNCHES['n'] += 1
     ev = _prof(kind, flops, desc)
-    _lib.check(_lib.load().dvd_conv2d_nhwc(ctypes.byref(desc), _ptr(x), _ptr(w_img), _ptr(bias), _ptr(g), _ptr(b), _ptr(m), _ptr(v),
-                                           _ptr(res), _ptr(res2), _ptr(mask), _ptr(y), _stream()), 'dvd_conv2d_nhwc')
+    ws = conv_workspace(x.device)
+    _lib.check(_lib.load().dvd_conv2d_nhwc_ws(ctypes.byref(desc), _ptr(x), _ptr(w_img), _ptr(bias), _ptr(g), _ptr(b), _ptr(m), _ptr(v),
+                                              _ptr(res), _ptr(res2), _ptr(mask), _ptr(y), _ptr(ws), ws.numel() * 4 if ws is not None else 0,
+                                              _stream()), 'dvd_conv2d_nhwc_ws')
     if ev is not None:
         ev.record()
     return y
@@ -122,6 +142,68 @@ def pack_weight(weight, groups=1, bn=None, out_fwd=None, out_bwd=None, want_fwd=
                                            _ptr(out_bwd if want_bwd else None), co, ci, kh, groups, kblock, _ptr(g), _ptr(v), float(eps),
                                            _stream()), 'dvd_conv2d_pack')
     return (out_fwd if want_fwd else None), (out_bwd if want_bwd else None)
+
+
+class PackTable:
+    """Every convolution of a net packed by ONE launch per step (dvd_conv2d_pack_batch): a device-resident table of
+    dvd_pack_item, rebuilt only when a parameter, BatchNorm buffer or image tensor has moved."""
+
+    def __init__(self, convs):
+        self.convs = list(convs)
+        self.key = None
+        self.table = None
+        self.total = 0
+
+    def _key(self):
+        k = []
+        for c in self.convs:
+            k.append(c.conv.weight.data_ptr())
+            k.append(c.w_fwd.data_ptr() if c.w_fwd is not None else 0)
+            k.append(c.w_bwd.data_ptr() if c.w_bwd is not None else 0)
+            if c.bn is not None:
+                k.append(c.bn.weight.data_ptr())
+                k.append(c.bn.running_var.data_ptr())
+        return tuple(k)
+
+    def _build(self, need_bwd):
+        lib = _lib.load()
+        items = (_lib.PackItem * len(self.convs))()
+        blk = 0
+        for it, c in zip(items, self.convs):
+            w = c.conv.weight
+            co, cil, kh, kw = w.shape
+            ci = cil * c.groups
+            dev = w.device
+            if c.w_fwd is None:
+                c.w_fwd = torch.empty(kh * kw, co, c.kblock if c.kblock else ci, dtype=torch.float32, device=dev)
+            if need_bwd and c.w_bwd is None:
+                c.w_bwd = torch.empty(kh * kw, ci, c.kblock if c.kblock else co, dtype=torch.float32, device=dev)
+            st = w.stride()
+            it.weight, it.w_fwd, it.w_bwd = w.data_ptr(), c.w_fwd.data_ptr(), (c.w_bwd.data_ptr() if c.w_bwd is not None else None)
+            if c.bn is not None:
+                it.bn_gamma, it.bn_var, it.bn_eps = c.bn.weight.data_ptr(), c.bn.running_var.data_ptr(), float(c.bn.eps)
+            it.s_co, it.s_ci, it.s_ky, it.s_kx = st
+            it.Cout, it.Cin, it.ksize, it.groups, it.kblock = co, ci, kh, c.groups, c.kblock
+            it.blk0 = blk
+            nb = lib.dvd_conv2d_pack_blocks(co, ci, kh, c.groups, c.kblock)
+            if nb < 1:
+                raise ValueError('bad convolution shape in the pack table')
+            blk += nb
+        raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
+        self.table = raw.to(self.convs[0].conv.weight.device)
+        self.total = blk
+
+    def pack(self, need_bwd=True):
+        if not self.convs[0].conv.weight.is_cuda:
+            raise ValueError('dvd_b200 has no CPU path: the depth net must live on a CUDA device')
+        if need_bwd and any(c.w_bwd is None for c in self.convs):
+            self.key = None
+        if self.key is None or self.key != self._key():
+            self._build(need_bwd)
+            self.key = self._key()
+        LAUNCHES['n'] += 1
+        _lib.check(_lib.load().dvd_conv2d_pack_batch(_ptr(self.table), len(self.convs), self.total, int(bool(need_bwd)), _stream()),
+                   'dvd_conv2d_pack_batch')
 
 
 def wgrad_launch(desc, x, gy, dweight, ksize, groups=1, weight=None, bn=None, dgamma=None, flops=0.0, colsum=None, bn_mean=None):

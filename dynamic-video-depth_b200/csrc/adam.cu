@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                                                         float* __restrict__ m, float* __restrict__ v, long n, float lr,
                                                         float b1, float b2, float eps, float bc1, float bc2_sqrt,
                                                         float gscale, const float* __restrict__ bc_dev) {
+  DVD_PDL_ENTER();
   if (bc_dev) { bc1 = bc_dev[1]; bc2_sqrt = bc_dev[2]; }      // step counter kept on the device (CUDA-graph replays)
   const float step_size = lr / bc1;
   const long n4 = n >> 2;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
 
 // device-side step counter: state = {step (as float bits of an int), 1 - b1^step, sqrt(1 - b2^step)}
 __global__ void adam_tick_kernel(float* __restrict__ state, float b1, float b2) {
+  DVD_PDL_ENTER();
   const int step = __float_as_int(state[0]) + 1;
   state[0] = __int_as_float(step);
   state[1] = (float)(1.0 - pow((double)b1, (double)step));
@@ -64,7 +66,7 @@ extern "C" int dvd_adam_flat(float* p, const float* g, float* m, float* v, long 
   long cap = (long)dvd::num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  dvd::adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1,
+  dvd::launch(dvd::adam_flat_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1,
                                                                         (float)sqrt(bc2), gscale, nullptr);
   DVD_CUDA_LAUNCH_CHECK("adam_flat");
   return 0;
@@ -78,9 +80,9 @@ extern "C" int dvd_adam_flat_dev(float* p, const float* g, float* m, float* v, l
   long cap = (long)dvd::num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  dvd::adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_state, beta1, beta2);
+  dvd::launch(dvd::adam_tick_kernel, 1, 1, 0, (cudaStream_t)stream, step_state, beta1, beta2);
   DVD_CUDA_LAUNCH_CHECK("adam_tick");
-  dvd::adam_flat_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, gscale,
+  dvd::launch(dvd::adam_flat_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, 1.f, 1.f, gscale,
                                                                         step_state);
   DVD_CUDA_LAUNCH_CHECK("adam_flat");
   return 0;

@@ -1,5 +1,6 @@
 // Error reporting + device queries shared by every translation unit of libdvd_b200.so.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace dvd {
@@ -11,6 +12,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DVD_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 int num_sms() {

@@ -41,7 +41,39 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int num_sms();
 
+// ---- programmatic dependent launch --------------------------------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (unless DVD_PDL=0) and begins
+// with DVD_PDL_ENTER(): griddepcontrol.wait (the preceding grid of the stream has completed and its writes are visible), then
+// griddepcontrol.launch_dependents (the NEXT grid may be scheduled as soon as every CTA of this one has passed this point and
+// resources free up: its launch latency, CTA start-up, barrier / tensor-memory set-up overlap this grid's tail). Because each
+// kernel waits before it triggers, at most two grids of a stream are in flight and completion stays transitive: when a grid's
+// wait returns, every earlier grid of the stream has completed. Tensor-core kernels run their set-up BEFORE the wait.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem_bytes, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
+
 // ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define DVD_PDL_ENTER()            \
+  do {                             \
+    dvd::pdl_wait();               \
+    dvd::pdl_launch_dependents();  \
+  } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

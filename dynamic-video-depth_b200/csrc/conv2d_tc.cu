@@ -42,6 +42,7 @@ constexpr int kOffStg = kStages * kStageBytes;              // 8 warps x 1 buffe
 constexpr int kOffAff = kOffStg + 8 * kStgBytes;            // scale[256] | shift[256]
 constexpr int kOffBar = kOffAff + 2 * kMaxNT * 4;
 constexpr size_t kSmem = kOffBar + 256;
+constexpr int kWsFlagWords = 256;           // stream-K exchange area: flag words in front of the partial tiles
 
 struct ConvParams {
   dvd_conv_desc d;
@@ -64,6 +65,51 @@ struct ConvParams {
   int pair;                       // csize == 2 as ONE tcgen05 CTA pair (cta_group::2): M = 256 pixels per MMA, each CTA keeps its own
                                   // 128-pixel A tile and HALF of the weight tile in shared memory (the tensor core reads both halves),
                                   // so the per-SM shared-memory traffic of the weight operand - the measured bound - halves
+  int sk;                         // stream-K: the (tile, K-step) work list is cut into one contiguous range per cluster instead of
+                                  // whole tiles round-robin; a tile cut by a range boundary is finished by the cluster that owns its
+                                  // FIRST K-steps (it reaches that tile last), the others leave raw partial accumulators in `ws`
+  float* ws;                      // int flags[256] (zero when idle) | [gridDim.x][128][NT] partial tiles
+};
+
+// One segment of work: K-steps [k0, k1) of cluster tile `tile`. Data-parallel mode: whole tiles, round-robin over the clusters.
+// Stream-K mode: the cluster's contiguous range of the tile-major (tile, K-step) list; range boundaries that fall within 1/8 of a
+// tile boundary snap to it (a sliver is not worth a partial-tile exchange).
+struct SegIter {
+  long u, u1;
+  int tile, ntiles, step, ksteps, sk;
+  __device__ static long bound(long c, long n_clusters, long total, int ksteps) {
+    if (c >= n_clusters) return total;
+    long u = c * total / n_clusters;
+    const int r = (int)(u % ksteps);
+    if (r * 8 < ksteps) u -= r;
+    else if ((ksteps - r) * 8 < ksteps) u += ksteps - r;
+    return u;
+  }
+  __device__ SegIter(int sk_, int cluster_id, int n_clusters, int ntiles_, int ksteps_) : ntiles(ntiles_), step(n_clusters), ksteps(ksteps_), sk(sk_) {
+    tile = cluster_id;
+    if (sk) {
+      const long total = (long)ntiles * ksteps;
+      u = bound(cluster_id, n_clusters, total, ksteps);
+      u1 = bound(cluster_id + 1, n_clusters, total, ksteps);
+    } else {
+      u = u1 = 0;
+    }
+  }
+  __device__ bool next(int& t, int& k0, int& k1) {
+    if (!sk) {
+      if (tile >= ntiles) return false;
+      t = tile; k0 = 0; k1 = ksteps;
+      tile += step;
+      return true;
+    }
+    if (u >= u1) return false;
+    t = (int)(u / ksteps);
+    k0 = (int)(u - (long)t * ksteps);
+    const long left = u1 - u;
+    k1 = (left < (long)(ksteps - k0)) ? k0 + (int)left : ksteps;
+    u += k1 - k0;
+    return true;
+  }
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
@@ -276,6 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
   tc_fence_after();
   if (P.csize > 1) cluster_sync_all();         // every CTA's barriers exist before a peer's multicast can reach them
   const uint32_t tmem = *tmem_holder;
+  DVD_PDL_ENTER();                             // set-up done: now wait for the producer of the operands
 
   const int crank = P.csize > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / P.csize, n_clusters = gridDim.x / P.csize;
@@ -292,13 +339,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = cluster_id; tile < ntiles; tile += n_clusters) {
+      SegIter seg(P.sk, cluster_id, n_clusters, ntiles, ksteps);
+      int tile, k0, k1;
+      while (seg.next(tile, k0, k1)) {
         const Tile T = decode_tile(P, tile, m_tiles, mgroups, crank);
         const int kbase = P.d.kblock ? (T.n0 / P.d.kblock) * P.d.kblock : 0;
         const int ws = T.w0 * P.d.stride, hs = T.h0 * P.d.stride;
-        for (int t = 0; t < P.d.ntaps; ++t) {
+        int t = k0 / P.kchunks, kc = k0 - t * P.kchunks;
+        for (int k = k0; k < k1; ++t, kc = 0) {
           const int dy = P.d.dy[t], dx = P.d.dx[t], wt = P.d.wt[t];
-          for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
+          for (; kc < P.kchunks && k < k1; ++kc, ++k, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
             uint8_t* st = smem + (size_t)s * kStageBytes;
             mbar_wait(&empty[s], ph ^ 1u);            // every CTA of the cluster has drained this stage
@@ -325,12 +375,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     if (lane == 0 && !(kPair && crank != 0)) {
       const uint32_t idesc = make_idesc_tf32(kPair ? 256 : 128, P.NT);
       uint32_t it = 0, lt = 0;
-      for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
+      SegIter seg(P.sk, cluster_id, n_clusters, ntiles, ksteps);
+      int tile, k0, k1;
+      for (; seg.next(tile, k0, k1); ++lt) {
         const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
         mbar_wait(&acc_empty[buf], aph ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem + buf * (uint32_t)kMaxNT;
-        for (int k = 0; k < ksteps; ++k, ++it) {
+        for (int k = 0; k < k1 - k0; ++k, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
           mbar_wait(&full[s], ph);
           tc_fence_after();
@@ -368,8 +420,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
       else mbar_arrive(&acc_empty[b]);
     };
     uint32_t lt = 0;
-    for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
+    SegIter seg(P.sk, cluster_id, n_clusters, ntiles, ksteps);
+    int tile, k0, k1;
+    // stream-K exchange area P.ws: kWsFlagWords flag words (one per CTA, zero when idle - fixed place, so that a launch with another
+    // tile shape never finds stale data there), then one partial tile [128][NT] per CTA
+    for (; seg.next(tile, k0, k1); ++lt) {
       const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
+      if (k0 > 0) {
+        // ---- partial tile (its first K-steps belong to an earlier cluster): raw accumulators -> exchange area, raise the flag ----
+        mbar_wait(&acc_full[buf], aph);
+        tc_fence_after();
+        const uint32_t d = tmem + buf * (uint32_t)kMaxNT + lane_base;
+        // layout of a partial tile: [16-byte channel chunk][row] - the 32 rows of a warp store 512 contiguous bytes per instruction
+        float* wrow = P.ws + kWsFlagWords + (size_t)blockIdx.x * 128 * P.NT + (size_t)row * 4;
+        for (int c0 = hsel * 32; c0 < P.NT; c0 += 64) {
+          uint32_t r[32];
+          tmem_ld32(d + c0, r);
+          tmem_ld_wait();
+          if (c0 + 64 >= P.NT) release_acc(buf);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + (size_t)(c0 + j) * 128), "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]),
+                         "r"(r[j + 3])
+                         : "memory");
+        }
+        if (hsel * 32 >= P.NT) release_acc(buf);
+        __threadfence();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (et == 0) {
+          int* ws_flags = reinterpret_cast<int*>(P.ws);
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ws_flags + blockIdx.x), "r"(1) : "memory");
+        }
+        continue;
+      }
+      // a tile this cluster starts but does not finish: the clusters whose ranges begin inside it deliver the rest
+      int n_part = 0;
+      if (k1 < ksteps) {
+        const long total = (long)ntiles * ksteps, tile_end = (long)(tile + 1) * ksteps;
+        while (cluster_id + 1 + n_part < n_clusters && SegIter::bound(cluster_id + 1 + n_part, n_clusters, total, ksteps) < tile_end) ++n_part;
+      }
       const Tile T = decode_tile(P, tile, m_tiles, mgroups, crank);
       const int h = T.h0 + row / P.TW, w = T.w0 + row % P.TW;
       const int yh = h * P.d.oy_mul + P.d.oy_add, yw = w * P.d.ox_mul + P.d.ox_add;
@@ -402,6 +491,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
         }
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after();
+        if (n_part) {
+          // the partial tiles were written long ago (they are the FIRST thing the later clusters do): this wait is short
+          if (et < n_part) {
+            const int* f = reinterpret_cast<const int*>(P.ws) + (cluster_id + 1 + et) * P.csize + crank;
+            int v = 0;
+            const long long t0 = clock64();
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              if (!v && clock64() - t0 > 4000000000LL) {
+                printf("dvd_b200: conv2d_tc_kernel: stream-K partial tile never arrived (block %d)\n", blockIdx.x);
+                __trap();
+              }
+            } while (!v);
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          // fold the partial tiles into the accumulator (tensor memory, this thread's own row and channel blocks); the regular
+          // epilogue below then runs unchanged
+          const uint32_t dd = tmem + buf * (uint32_t)kMaxNT + lane_base;
+          for (int c0 = hsel * 32; c0 < P.NT; c0 += 64) {
+            for (int hh = 0; hh < 32; hh += 16) {
+              uint32_t r[16];
+              tmem_ld16(dd + c0 + hh, r);
+              tmem_ld_wait();
+              for (int pi = 0; pi < n_part; ++pi) {
+                const float* prow = P.ws + kWsFlagWords + (size_t)((cluster_id + 1 + pi) * P.csize + crank) * 128 * P.NT + (size_t)row * 4 +
+                                    (size_t)(c0 + hh) * 128;
+                float4 a[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  // strong (gpu-scope) load: the tile was written by another SM; a weak load may be served from a stale L1 line
+                  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                               : "=f"(a[j].x), "=f"(a[j].y), "=f"(a[j].z), "=f"(a[j].w)
+                               : "l"(prow + (size_t)j * 512)
+                               : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + a[j].x);
+                  r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + a[j].y);
+                  r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + a[j].z);
+                  r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + a[j].w);
+                }
+              }
+              tmem_st16(dd + c0 + hh, r);
+            }
+          }
+          tmem_st_wait();
+        }
         const uint32_t d = tmem + buf * (uint32_t)kMaxNT + lane_base;
         const int bh0 = T.h0 + (q * 32) / P.TW, bw0 = T.w0 + (q * 32) % P.TW;
         for (int c0 = hsel * 32; c0 < P.NT; c0 += 64) {
@@ -428,6 +565,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
           }
         }
         if (hsel * 32 >= P.NT) release_acc(buf);  // NT = 32: the odd warps have no block, but owe their arrival
+        if (n_part) {
+          // every reader is done with the partial tiles: lower the flags for the next launch (ordered by the kernel boundary)
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (et < n_part) reinterpret_cast<int*>(P.ws)[(cluster_id + 1 + et) * P.csize + crank] = 0;
+        }
       } else {
         if (has_aff) {
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -488,6 +630,7 @@ __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict_
                                                         float* __restrict__ out_fwd, float* __restrict__ out_bwd, int Cout, int Cin,
                                                         int k, int cpg, int kblock, const float* __restrict__ gamma,
                                                         const float* __restrict__ var, float eps) {
+  DVD_PDL_ENTER();
   // both images have k*k * C * cols elements when Cin == Cout or dense; they are walked with one index each
   const int opg = Cout / (Cin / cpg);        // out-channels per group
   for (int mode = 0; mode < 2; ++mode) {
@@ -507,6 +650,46 @@ __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict_
       if (co / opg == ci / cpg) {                                  // same group (dense: one group)
         v = w[co * s_co + (ci % cpg) * s_ci + ky * s_ky + kx * s_kx];
         if (mode && gamma) v *= gamma[co] * rsqrtf(var[co] + eps);
+      }
+      out[i] = round_tf32(v);
+    }
+  }
+}
+
+// All layers of a net in ONE launch (the weights change every optimisation step, so every step re-packs ~250 images: as single
+// launches that is 123 grids of a few microseconds each). items[] lives in device memory; item i owns the blocks
+// [blk0[i], blk0[i+1]) of the grid, each block packs kPackChunk consecutive elements of both images.
+constexpr int kPackChunk = 2048;
+__global__ void __launch_bounds__(256) conv_pack_batch_kernel(const dvd_pack_item* __restrict__ items, int n_items, int want_bwd) {
+  DVD_PDL_ENTER();
+  int lo = 0, hi = n_items - 1;
+  while (lo < hi) {                       // last item whose first block is <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].blk0 <= (long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const dvd_pack_item it = items[lo];
+  const int Cout = it.Cout, Cin = it.Cin, k = it.ksize, kblock = it.kblock;
+  const int cpg = Cin / it.groups, opg = Cout / it.groups;
+  const long base = ((long)blockIdx.x - it.blk0) * kPackChunk;
+  for (int mode = 0; mode < 2; ++mode) {
+    float* out = mode ? (want_bwd ? it.w_bwd : nullptr) : it.w_fwd;
+    if (!out) continue;
+    const int rows = mode ? Cin : Cout;
+    const int cols = kblock ? kblock : (mode ? Cout : Cin);
+    const long n = (long)k * k * rows * cols;
+    for (int e = threadIdx.x; e < kPackChunk; e += 256) {
+      const long i = base + e;
+      if (i >= n) break;
+      const int c = (int)(i % cols);
+      const long q = i / cols;
+      const int r = (int)(q % rows), t = (int)(q / rows);
+      const int ky = t / k, kx = t - ky * k;
+      const int cabs = kblock ? (r / kblock) * kblock + c : c;
+      const int co = mode ? cabs : r, ci = mode ? r : cabs;
+      float v = 0.f;
+      if (co / opg == ci / cpg) {
+        v = it.weight[co * it.s_co + (ci % cpg) * it.s_ci + ky * it.s_ky + kx * it.s_kx];
+        if (mode && it.bn_gamma) v *= it.bn_gamma[co] * rsqrtf(it.bn_var[co] + it.bn_eps);
       }
       out[i] = round_tf32(v);
     }
@@ -603,6 +786,7 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
   tc_fence_after();
   if (P.csize > 1) cluster_sync_all();
   const uint32_t tmem = *tmem_holder;
+  DVD_PDL_ENTER();
 
   // this CTA: output tile (tap, 128 M-channels, NT N-channels) and a contiguous range of pixel tiles.
   // blockIdx.x = ((tap, M group, N tile) * ksplit + part) * csize + rank, M block = group * csize + rank
@@ -832,13 +1016,15 @@ int launch_clustered(void (*kernel)(Args...), int grid, int threads, size_t smem
   cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2u : 1u;
   DVD_CUDA_CALL(cudaLaunchKernelEx(&cfg, kernel, args...));
   return 0;
 }
@@ -872,9 +1058,20 @@ int max_clusters(K kernel, int threads, size_t smem_bytes, int csize) {
 
 using namespace dvd;
 
+extern "C" size_t dvd_conv2d_workspace_bytes(void) {
+  // one partial tile [128][256] fp32 and one flag per resident CTA
+  return (size_t)kWsFlagWords * sizeof(int) + (size_t)num_sms() * 128 * kMaxNT * sizeof(float);
+}
+
 extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const float* w_img, const float* bias, const float* bn_gamma,
                                const float* bn_beta, const float* bn_mean, const float* bn_var, const float* res, const float* res2,
                                const float* mask, float* y, void* stream) {
+  return dvd_conv2d_nhwc_ws(desc, x, w_img, bias, bn_gamma, bn_beta, bn_mean, bn_var, res, res2, mask, y, nullptr, 0, stream);
+}
+
+extern "C" int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, const float* w_img, const float* bias, const float* bn_gamma,
+                                  const float* bn_beta, const float* bn_mean, const float* bn_var, const float* res, const float* res2,
+                                  const float* mask, float* y, void* workspace, size_t workspace_bytes, void* stream) {
   DVD_ARG_CHECK(desc && x && w_img && y, "null pointer");
   ConvParams P{};
   P.d = *desc;
@@ -958,8 +1155,38 @@ extern "C" int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const 
     mapY = mapA;
   }
   const long ctiles = ((m_tiles_h + P.csize - 1) / P.csize) * (d.Cout / P.NT);      // cluster tiles
-  long nclusters = max_clusters(conv2d_tc_kernel<false>, kThreads, kSmem, P.csize);
-  if (ctiles < nclusters) nclusters = ctiles;
+  const long full = max_clusters(conv2d_tc_kernel<false>, kThreads, kSmem, P.csize);
+  long nclusters = ctiles < full ? ctiles : full;
+  // stream-K when whole tiles would leave a large part of the machine idle in the last (or only) wave: cut the (tile, K-step)
+  // list into equal contiguous ranges instead. Needs the caller's exchange area (zeroed once; the kernel leaves it zeroed where
+  // it matters: the flags). A range is at least max(8, ksteps / 4) K-steps long, so a tile is shared by at most ~4 clusters.
+  P.sk = 0;
+  P.ws = nullptr;
+  {
+    const long ksteps = (long)d.ntaps * P.kchunks, total = ctiles * ksteps;
+    const long waves = (ctiles + full - 1) / full;
+    const double eff = (double)ctiles / (double)(waves * full);
+    const char* ev = getenv("DVD_CONV_STREAMK");
+    const bool allowed = !(ev && atoi(ev) == 0);
+    if (allowed && workspace && P.tma_store && ksteps >= 8 && eff < 0.88) {
+      const long min_units = ksteps / 4 > 8 ? ksteps / 4 : 8;
+      long nc = total / min_units;
+      if (nc > full) nc = full;
+      const size_t need = (size_t)kWsFlagWords * sizeof(int) + (size_t)nc * P.csize * 128 * (size_t)P.NT * sizeof(float);
+      // the exchange (partial tiles through L2, a short serial tail in the finishing CTA) costs about as much as 50 K-steps
+      // (measured: profiles/r3_streamk_table.txt): only layers with few tiles and a long K loop gain - the 3x3 layerN_rn
+      // convolutions at 1/16 and 1/32 resolution (2.6x / 1.7x faster), not the 32-step 1x1 layers of the encoder
+      const long dp_steps = waves * ksteps, sk_steps = (total + nc - 1) / nc;
+      if ((nc > nclusters || (nc == nclusters && waves > 1)) && dp_steps - sk_steps >= 64) {
+        DVD_ARG_CHECK(aligned16(workspace), "workspace must be 16-byte aligned");
+        if (need <= workspace_bytes && nc * P.csize <= kWsFlagWords) {
+          P.sk = 1;
+          P.ws = static_cast<float*>(workspace);
+          nclusters = nc;
+        }
+      }
+    }
+  }
   if (int e = P.pair ? launch_clustered(conv2d_tc_kernel<true>, (int)nclusters * P.csize, kThreads, kSmem, P.csize, (cudaStream_t)stream,
                                         mapA, mapW, mapY, P)
                      : launch_clustered(conv2d_tc_kernel<false>, (int)nclusters * P.csize, kThreads, kSmem, P.csize, (cudaStream_t)stream,
@@ -982,9 +1209,22 @@ extern "C" int dvd_conv2d_pack(const float* weight, long stride_co, long stride_
   const long n = (long)ksize * ksize * (Cout > Cin ? Cout : Cin) * (kblock ? kblock : (Cout > Cin ? Cin : Cout));
   int blocks = (int)((n + 255) / 256);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
-  conv_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(weight, stride_co, stride_ci, stride_ky, stride_kx, w_fwd, w_bwd, Cout, Cin,
+  dvd::launch(conv_pack_kernel, blocks, 256, 0, (cudaStream_t)stream, weight, stride_co, stride_ci, stride_ky, stride_kx, w_fwd, w_bwd, Cout, Cin,
                                                            ksize, cpg, kblock, bn_gamma, bn_var, bn_eps);
   DVD_CUDA_LAUNCH_CHECK("conv_pack_kernel");
+  return 0;
+}
+
+extern "C" long dvd_conv2d_pack_blocks(int Cout, int Cin, int ksize, int groups, int kblock) {
+  if (Cout < 1 || Cin < 1 || ksize < 1 || groups < 1) return -1;
+  const long n = (long)ksize * ksize * (Cout > Cin ? Cout : Cin) * (kblock ? kblock : (Cout > Cin ? Cin : Cout));
+  return (n + kPackChunk - 1) / kPackChunk;
+}
+
+extern "C" int dvd_conv2d_pack_batch(const dvd_pack_item* items_dev, int n_items, long total_blocks, int want_bwd, void* stream) {
+  DVD_ARG_CHECK(items_dev && n_items >= 1 && total_blocks >= 1 && total_blocks < (1L << 31), "bad pack table");
+  dvd::launch(conv_pack_batch_kernel, (unsigned)total_blocks, 256, 0, (cudaStream_t)stream, items_dev, n_items, want_bwd);
+  DVD_CUDA_LAUNCH_CHECK("conv_pack_batch_kernel");
   return 0;
 }
 

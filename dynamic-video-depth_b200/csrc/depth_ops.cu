@@ -31,6 +31,7 @@ unsigned blocks_for(long n, int per_sm = 16) {
 }
 
 __global__ void __launch_bounds__(kThreads) round_kernel(const float4* __restrict__ x, float4* __restrict__ y, long n4) {
+  DVD_PDL_ENTER();
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) y[i] = round4(x[i]);
 }
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(kThreads) relu_bwd_colsum_kernel(const float4*
                                                                    const float* __restrict__ mean, const float* __restrict__ var,
                                                                    float eps, float* __restrict__ dgamma, long P, int c4, int cgb,
                                                                    int round_out) {
+  DVD_PDL_ENTER();
   __shared__ float red[kThreads][4];
   const int tx = threadIdx.x % cgb, ty = threadIdx.x / cgb, rows = kThreads / cgb;
   const int cg = blockIdx.y * cgb + tx;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(kThreads) relu_bwd_colsum_kernel(const float4*
 // ---- MaxPool2d(3, stride 2, padding 1), NHWC; idx = position (0..8) of the first maximum inside the window -----------
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y,
                                                                uchar4* __restrict__ idx, int N, int H, int W, int OH, int OW, int c4) {
+  DVD_PDL_ENTER();
   const long total = (long)N * OH * OW * c4;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float4* __r
 
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float4* __restrict__ g, const uchar4* __restrict__ idx,
                                                                float4* __restrict__ gx, int N, int H, int W, int OH, int OW, int c4) {
+  DVD_PDL_ENTER();
   const long total = (long)N * H * W * c4;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ beta, const float* __restrict__ mean,
                                                        const float* __restrict__ var, float eps, float3 nmean, float3 nrstd,
                                                        float* __restrict__ y, int N, int H, int W, int OH, int OW, int round_out) {
+  DVD_PDL_ENTER();
   __shared__ float wsm[kStemTaps][64];                          // [c*49 + ky*7 + kx][co]
   __shared__ float patch[3][kStemPH][kStemPW];
   __shared__ float aff[2][64];
@@ -226,6 +231,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
                                                          const float* __restrict__ a0, float3 nmean, float3 nrstd,
                                                          float* __restrict__ dwu, float* __restrict__ bsum, int N, int H, int W, int OH,
                                                          int OW) {
+  DVD_PDL_ENTER();
   __shared__ float patch[3][kStemPH][kStemPW];
   __shared__ __align__(16) float gsm[128][64];
   const float nm[3] = {nmean.x, nmean.y, nmean.z}, nr[3] = {nrstd.x, nrstd.y, nrstd.z};
@@ -293,6 +299,7 @@ __global__ void __launch_bounds__(64) stem_wgrad_finalize_kernel(const float* __
                                                                  long s_ky, long s_kx, const float* __restrict__ gamma,
                                                                  const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  DVD_PDL_ENTER();
   const int co = threadIdx.x;
   const float rstd = rsqrtf(var[co] + eps), sc = gamma[co] * rstd;
   float dot = 0.f;
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(64) stem_wgrad_finalize_kernel(const float* __
 // ---- head: depth = 10000 / max(relu(<x[p,:], w> + b), 1e-2) ------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) head_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ b, float* __restrict__ depth, long P) {
+  DVD_PDL_ENTER();
   __shared__ float ws[32];
   if (threadIdx.x < 32) ws[threadIdx.x] = w[threadIdx.x];
   __syncthreads();
@@ -329,6 +337,7 @@ __global__ void __launch_bounds__(kThreads) head_bwd_kernel(const float4* __rest
                                                             const float* __restrict__ b, const float* __restrict__ gd,
                                                             float4* __restrict__ gx, float* __restrict__ gw, float* __restrict__ gb, long P,
                                                             int relu_mask, int round_out) {
+  DVD_PDL_ENTER();
   __shared__ float ws[32];
   __shared__ float red[kThreads / 32][33];
   if (threadIdx.x < 32) ws[threadIdx.x] = w[threadIdx.x];
@@ -386,7 +395,7 @@ using namespace dvd;
 
 extern "C" int dvd_round_tf32(const float* x, float* y, long n, void* stream) {
   DVD_ARG_CHECK(x && y && n > 0 && n % 4 == 0 && aligned16(x) && aligned16(y), "needs 16-byte aligned buffers and n %% 4 == 0");
-  round_kernel<<<blocks_for(n / 4), kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, n / 4);
+  dvd::launch(round_kernel, blocks_for(n / 4), kThreads, 0, (cudaStream_t)stream, (const float4*)x, (float4*)y, n / 4);
   DVD_CUDA_LAUNCH_CHECK("round_kernel");
   return 0;
 }
@@ -406,7 +415,7 @@ extern "C" int dvd_relu_bwd_colsum(const float* g, const float* y, float* gm, fl
   if (gx_blocks > cap) gx_blocks = cap;
   if (gx_blocks < 1) gx_blocks = 1;
   dim3 grid((unsigned)gx_blocks, (unsigned)((c4 + cgb - 1) / cgb));
-  relu_bwd_colsum_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float4*)g, (const float4*)y, (float4*)gm, colsum, bn_mean,
+  dvd::launch(relu_bwd_colsum_kernel, grid, kThreads, 0, (cudaStream_t)stream, (const float4*)g, (const float4*)y, (float4*)gm, colsum, bn_mean,
                                                                     bn_var, bn_eps, dgamma, P, c4, cgb, round_out);
   DVD_CUDA_LAUNCH_CHECK("relu_bwd_colsum_kernel");
   return 0;
@@ -416,7 +425,7 @@ extern "C" int dvd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx
   DVD_ARG_CHECK(x && y && idx && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad arguments (C must be a multiple of 4)");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long total = (long)N * OH * OW * (C / 4);
-  maxpool_fwd_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, (uchar4*)idx, N, H, W, OH, OW,
+  dvd::launch(maxpool_fwd_kernel, blocks_for(total), kThreads, 0, (cudaStream_t)stream, (const float4*)x, (float4*)y, (uchar4*)idx, N, H, W, OH, OW,
                                                                              C / 4);
   DVD_CUDA_LAUNCH_CHECK("maxpool_fwd_kernel");
   return 0;
@@ -426,7 +435,7 @@ extern "C" int dvd_maxpool3x3s2_bwd(const float* g, const unsigned char* idx, fl
   DVD_ARG_CHECK(g && gx && idx && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad arguments (C must be a multiple of 4)");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long total = (long)N * H * W * (C / 4);
-  maxpool_bwd_kernel<<<blocks_for(total), kThreads, 0, (cudaStream_t)stream>>>((const float4*)g, (const uchar4*)idx, (float4*)gx, N, H, W, OH,
+  dvd::launch(maxpool_bwd_kernel, blocks_for(total), kThreads, 0, (cudaStream_t)stream, (const float4*)g, (const uchar4*)idx, (float4*)gx, N, H, W, OH,
                                                                              OW, C / 4);
   DVD_CUDA_LAUNCH_CHECK("maxpool_bwd_kernel");
   return 0;
@@ -444,7 +453,7 @@ extern "C" int dvd_stem_fwd(const float* x_nchw, const float* weight, long s_co,
   const int ntiles = N * ((OH + kStemTH - 1) / kStemTH) * ((OW + kStemTW - 1) / kStemTW);
   int grid = num_sms() * 4;
   if (grid > ntiles) grid = ntiles;
-  stem_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, weight, s_co, s_ci, s_ky, s_kx, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps,
+  dvd::launch(stem_fwd_kernel, grid, 128, 0, (cudaStream_t)stream, x_nchw, weight, s_co, s_ci, s_ky, s_kx, bn_gamma, bn_beta, bn_mean, bn_var, bn_eps,
                                                         nm, nr, y, N, H, W, OH, OW, round_out);
   DVD_CUDA_LAUNCH_CHECK("stem_fwd_kernel");
   return 0;
@@ -464,9 +473,9 @@ extern "C" int dvd_stem_wgrad(const float* x_nchw, const float* g, const float* 
   const int ntiles = N * ((OH + kStemTH - 1) / kStemTH) * ((OW + kStemTW - 1) / kStemTW);
   int grid = num_sms() * 2;
   if (grid > ntiles) grid = ntiles;
-  stem_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, g, a0, nm, nr, scratch, scratch + kStemTaps * 64, N, H, W, OH, OW);
+  dvd::launch(stem_wgrad_kernel, grid, 256, 0, (cudaStream_t)stream, x_nchw, g, a0, nm, nr, scratch, scratch + kStemTaps * 64, N, H, W, OH, OW);
   DVD_CUDA_LAUNCH_CHECK("stem_wgrad_kernel");
-  stem_wgrad_finalize_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(scratch, scratch + kStemTaps * 64, weight, dweight, s_co, s_ci, s_ky, s_kx,
+  dvd::launch(stem_wgrad_finalize_kernel, 1, 64, 0, (cudaStream_t)stream, scratch, scratch + kStemTaps * 64, weight, dweight, s_co, s_ci, s_ky, s_kx,
                                                                 bn_gamma, bn_mean, bn_var, bn_eps, dgamma, dbeta);
   DVD_CUDA_LAUNCH_CHECK("stem_wgrad_finalize_kernel");
   return 0;
@@ -474,7 +483,7 @@ extern "C" int dvd_stem_wgrad(const float* x_nchw, const float* g, const float* 
 
 extern "C" int dvd_head_fwd(const float* x, const float* w, const float* b, float* depth, long P, void* stream) {
   DVD_ARG_CHECK(x && w && b && depth && P > 0 && aligned16(x), "bad arguments");
-  head_fwd_kernel<<<blocks_for(P), kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, w, b, depth, P);
+  dvd::launch(head_fwd_kernel, blocks_for(P), kThreads, 0, (cudaStream_t)stream, (const float4*)x, w, b, depth, P);
   DVD_CUDA_LAUNCH_CHECK("head_fwd_kernel");
   return 0;
 }
@@ -482,7 +491,7 @@ extern "C" int dvd_head_fwd(const float* x, const float* w, const float* b, floa
 extern "C" int dvd_head_bwd(const float* x, const float* w, const float* b, const float* g_depth, float* gx, float* gw, float* gb, long P,
                             int relu_mask, int round_out, void* stream) {
   DVD_ARG_CHECK(x && w && b && g_depth && gx && gw && gb && P > 0 && aligned16(x) && aligned16(gx), "bad arguments");
-  head_bwd_kernel<<<blocks_for(P, 4), kThreads, 0, (cudaStream_t)stream>>>((const float4*)x, w, b, g_depth, (float4*)gx, gw, gb, P, relu_mask, round_out);
+  dvd::launch(head_bwd_kernel, blocks_for(P, 4), kThreads, 0, (cudaStream_t)stream, (const float4*)x, w, b, g_depth, (float4*)gx, gw, gb, P, relu_mask, round_out);
   DVD_CUDA_LAUNCH_CHECK("head_bwd_kernel");
   return 0;
 }

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(kElemThreads) bn_act_fwd_kernel(const float4* 
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ mean, const float* __restrict__ var,
                                                                   float eps, float4* __restrict__ y, long n4, int c4, int relu) {
+  DVD_PDL_ENTER();
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const int c = (int)(i % c4) * 4;
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(kElemThreads) bn_act_bwd_kernel(const float4* 
                                                                   float eps, float4* __restrict__ gx, float4* __restrict__ gres,
                                                                   float* __restrict__ ggamma, float* __restrict__ gbeta, long P,
                                                                   int c4, int cgb, int relu) {
+  DVD_PDL_ENTER();
   __shared__ float red[kElemThreads][8];
   const int tx = threadIdx.x % cgb, ty = threadIdx.x / cgb, rows = kElemThreads / cgb;
   const int cg = blockIdx.y * cgb + tx;        // channel group (4 channels)
@@ -115,6 +117,7 @@ __device__ __forceinline__ float src_index(int dst, float scale, bool align) {
 __global__ void __launch_bounds__(kElemThreads) upsample2x_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N,
                                                                       int H, int W, int c4, float sh, float sw, int align,
                                                                       int round_out) {
+  DVD_PDL_ENTER();
   const int OH = 2 * H, OW = 2 * W;
   const long total = (long)N * OH * OW * c4;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(kElemThreads) upsample2x_fwd_kernel(const floa
 __global__ void __launch_bounds__(kElemThreads) upsample2x_bwd_kernel(const float4* __restrict__ g, float4* __restrict__ gx, int N,
                                                                       int H, int W, int c4, float sh, float sw, int align,
                                                                       int round_out) {
+  DVD_PDL_ENTER();
   const int OH = 2 * H, OW = 2 * W;
   const long total = (long)N * H * W * c4;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -205,7 +209,7 @@ extern "C" int dvd_bn_act_fwd(const float* x, const float* res, const float* gam
   DVD_ARG_CHECK(aligned16(x) && aligned16(y) && (!res || aligned16(res)) && aligned16(gamma) && aligned16(beta) &&
                     aligned16(mean) && aligned16(var), "buffers must be 16-byte aligned");
   const long n4 = P * (C / 4);
-  bn_act_fwd_kernel<<<blocks_for(n4), kElemThreads, 0, (cudaStream_t)stream>>>(
+  dvd::launch(bn_act_fwd_kernel, blocks_for(n4), kElemThreads, 0, (cudaStream_t)stream, 
       (const float4*)x, (const float4*)res, gamma, beta, mean, var, eps, (float4*)y, n4, C / 4, relu);
   DVD_CUDA_LAUNCH_CHECK("bn_act_fwd");
   return 0;
@@ -227,7 +231,7 @@ extern "C" int dvd_bn_act_bwd(const float* g, const float* x, const float* y, co
   if (gx_blocks > cap) gx_blocks = cap;
   if (gx_blocks < 1) gx_blocks = 1;
   dim3 grid((unsigned)gx_blocks, (unsigned)((c4 + cgb - 1) / cgb));
-  bn_act_bwd_kernel<<<grid, kElemThreads, 0, (cudaStream_t)stream>>>((const float4*)g, (const float4*)x, (const float4*)y, gamma, mean,
+  dvd::launch(bn_act_bwd_kernel, grid, kElemThreads, 0, (cudaStream_t)stream, (const float4*)g, (const float4*)x, (const float4*)y, gamma, mean,
                                                                      var, eps, (float4*)gx, (float4*)gres, ggamma, gbeta, P, c4, cgb,
                                                                      relu);
   DVD_CUDA_LAUNCH_CHECK("bn_act_bwd");
@@ -239,7 +243,7 @@ extern "C" int dvd_upsample2x_fwd(const float* x, float* y, int N, int H, int W,
   const float sh = align_corners ? (H > 1 ? (float)(H - 1) / (2 * H - 1) : 0.f) : 0.5f;
   const float sw = align_corners ? (W > 1 ? (float)(W - 1) / (2 * W - 1) : 0.f) : 0.5f;
   const long total = (long)N * 4 * H * W * (C / 4);
-  upsample2x_fwd_kernel<<<blocks_for(total), kElemThreads, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4, sh,
+  dvd::launch(upsample2x_fwd_kernel, blocks_for(total), kElemThreads, 0, (cudaStream_t)stream, (const float4*)x, (float4*)y, N, H, W, C / 4, sh,
                                                                                     sw, align_corners, round_out);
   DVD_CUDA_LAUNCH_CHECK("upsample2x_fwd");
   return 0;
@@ -250,7 +254,7 @@ extern "C" int dvd_upsample2x_bwd(const float* g, float* gx, int N, int H, int W
   const float sh = align_corners ? (H > 1 ? (float)(H - 1) / (2 * H - 1) : 0.f) : 0.5f;
   const float sw = align_corners ? (W > 1 ? (float)(W - 1) / (2 * W - 1) : 0.f) : 0.5f;
   const long total = (long)N * H * W * (C / 4);
-  upsample2x_bwd_kernel<<<blocks_for(total), kElemThreads, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)gx, N, H, W, C / 4, sh,
+  dvd::launch(upsample2x_bwd_kernel, blocks_for(total), kElemThreads, 0, (cudaStream_t)stream, (const float4*)g, (float4*)gx, N, H, W, C / 4, sh,
                                                                                     sw, align_corners, round_out);
   DVD_CUDA_LAUNCH_CHECK("upsample2x_bwd");
   return 0;

@@ -246,6 +246,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads) unproject_fwd_kernel(const float* __restrict__ depth,
                                                                  const float* __restrict__ poses,
                                                                  float* __restrict__ P, int H, int W, int which) {
+  DVD_PDL_ENTER();
   __shared__ Pose ps;
   const int b = blockIdx.y;
   load_pose(ps, poses, b);
@@ -281,6 +282,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kThreads) unproject_bwd_kernel(const float* __restrict__ gP,
                                                                  const float* __restrict__ poses,
                                                                  float* __restrict__ gd, int H, int W, int which) {
+  DVD_PDL_ENTER();
   __shared__ Pose ps;
   const int b = blockIdx.y;
   load_pose(ps, poses, b);
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(kThreads, MINB) reproject_loss_fwd_kernel(
     const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
     const float* __restrict__ mask_2, const float* __restrict__ sf, const float* __restrict__ poses,
     dvd_loss_cfg cfg, float* __restrict__ partials, int H, int W) {
+  DVD_PDL_ENTER();
   __shared__ Pose ps;
   __shared__ float red[kThreads / 32][4];
   const int b = blockIdx.y;
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, MINB) reproject_loss_fwd_kernel(
 // deterministic final reduction (fixed order, double accumulation) + loss assembly
 __global__ void __launch_bounds__(256) reproject_finalize_kernel(const float* __restrict__ partials, int n_quads,
                                                                  dvd_loss_cfg cfg, float* __restrict__ scalars) {
+  DVD_PDL_ENTER();
   __shared__ double red[8][4];
   double acc[4] = {0, 0, 0, 0};
   for (int i = threadIdx.x; i < n_quads; i += blockDim.x) {
@@ -416,6 +420,7 @@ __global__ void __launch_bounds__(kThreads) reproject_loss_bwd_kernel(
     dvd_loss_cfg cfg, const float* __restrict__ scalars, float gscale, const float* __restrict__ gscale_dev,
     float* __restrict__ g_sf,
     float* __restrict__ g_d2, int H, int W) {
+  DVD_PDL_ENTER();
   __shared__ Pose ps;
   const int b = blockIdx.y;
   load_pose(ps, poses, b);
@@ -530,6 +535,7 @@ __global__ void __launch_bounds__(kThreads) reproject_materialize_kernel(
     float* __restrict__ sf_by_depth, float* __restrict__ warped_global_p2, float* __restrict__ warped_p2_camera_2,
     float* __restrict__ p1_camera_2, float* __restrict__ dflow, float* __restrict__ staticflow,
     float* __restrict__ depth_image, float* __restrict__ depth_warp, int H, int W) {
+  DVD_PDL_ENTER();
   __shared__ Pose ps;
   const int b = blockIdx.y;
   load_pose(ps, poses, b);
@@ -584,6 +590,7 @@ __global__ void __launch_bounds__(kThreads) reproject_materialize_bwd_kernel(
     const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
     const float* __restrict__ sf, const float* __restrict__ poses, MatGrads G, float* __restrict__ g_d1,
     float* __restrict__ g_d2, float* __restrict__ g_sf, int H, int W) {
+  DVD_PDL_ENTER();
   __shared__ Pose ps;
   const int b = blockIdx.y;
   load_pose(ps, poses, b);
@@ -682,6 +689,7 @@ __constant__ PoseC c_pose[kPoseSlots][kPosePairs];
 __device__ PoseC g_pose_stage[kPoseSlots][kPosePairs];
 
 __global__ void pose_prep_kernel(const float* __restrict__ poses, int B, int slot) {
+  DVD_PDL_ENTER();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* p = poses + (size_t)b * DVD_POSE_STRIDE;
@@ -909,6 +917,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) reproject_loss_fwd_staged
     const float* __restrict__ depth_1, const float* __restrict__ depth_2, const float* __restrict__ flow,
     const float* __restrict__ mask_2, const float* __restrict__ sf, dvd_loss_cfg cfg, float* __restrict__ partials,
     int H, int W, int slot, int b0, int nb, int tiles_per_pair) {
+  DVD_PDL_ENTER();
   using namespace tc;
   constexpr int VEC = 2 * NP, TILE = StagedCfg<NP>::TILE, FLOATS = StagedCfg<NP>::FLOATS;
   extern __shared__ __align__(128) float stage_mem[];
@@ -1094,6 +1103,7 @@ __global__ void __launch_bounds__(kThreads + 32, MINB) reproject_loss_bwd_staged
     const float* __restrict__ mask_2, const float* __restrict__ sf, dvd_loss_cfg cfg, const float* __restrict__ scalars,
     float gscale, const float* __restrict__ gscale_dev, float* __restrict__ g_sf, float* __restrict__ g_d2, int H, int W,
     int slot, int b0, int nb, int tiles_per_pair) {
+  DVD_PDL_ENTER();
   using namespace tc;
   constexpr int VEC = 2 * NP, TILE = StagedCfg<NP>::TILE, FLOATS = StagedCfg<NP>::FLOATS;
   extern __shared__ __align__(128) float stage_mem[];
@@ -1240,7 +1250,7 @@ static int stage_poses(const float* poses, int b0, int nb, cudaStream_t st, int*
   DVD_CUDA_CALL(cudaStreamIsCapturing(st, &cap));
   if (cap == cudaStreamCaptureStatusNone && S->used[slot])
     DVD_CUDA_CALL(cudaStreamWaitEvent(st, S->ev[slot], 0));   // previous reader of this slot is done
-  pose_prep_kernel<<<1, kPosePairs, 0, st>>>(poses + (size_t)b0 * DVD_POSE_STRIDE, nb, slot);
+  dvd::launch(pose_prep_kernel, 1, kPosePairs, 0, st, poses + (size_t)b0 * DVD_POSE_STRIDE, nb, slot);
   DVD_CUDA_LAUNCH_CHECK("pose_prep");
   DVD_CUDA_CALL(cudaMemcpyToSymbolAsync(c_pose, S->stage + (size_t)slot * kPosePairs, (size_t)nb * sizeof(PoseC),
                                         (size_t)slot * kPosePairs * sizeof(PoseC), cudaMemcpyDeviceToDevice, st));
@@ -1290,9 +1300,9 @@ extern "C" int dvd_unproject_fwd(const float* depth, const float* poses, float* 
   cudaStream_t st = (cudaStream_t)stream;
   int vec = pick_vec(B, H, W, {depth, P});
   const int ipp = H * W / vec;
-  if (vec == 4) unproject_fwd_kernel<4><<<grid_for(unproject_fwd_kernel<4>, B, ipp), kThreads, 0, st>>>(depth, poses, P, H, W, which);
-  else if (vec == 2) unproject_fwd_kernel<2><<<grid_for(unproject_fwd_kernel<2>, B, ipp), kThreads, 0, st>>>(depth, poses, P, H, W, which);
-  else unproject_fwd_kernel<1><<<grid_for(unproject_fwd_kernel<1>, B, ipp), kThreads, 0, st>>>(depth, poses, P, H, W, which);
+  if (vec == 4) dvd::launch(unproject_fwd_kernel<4>, grid_for(unproject_fwd_kernel<4>, B, ipp), kThreads, 0, st, depth, poses, P, H, W, which);
+  else if (vec == 2) dvd::launch(unproject_fwd_kernel<2>, grid_for(unproject_fwd_kernel<2>, B, ipp), kThreads, 0, st, depth, poses, P, H, W, which);
+  else dvd::launch(unproject_fwd_kernel<1>, grid_for(unproject_fwd_kernel<1>, B, ipp), kThreads, 0, st, depth, poses, P, H, W, which);
   DVD_CUDA_LAUNCH_CHECK("unproject_fwd");
   return 0;
 }
@@ -1305,9 +1315,9 @@ extern "C" int dvd_unproject_bwd(const float* gP, const float* poses, float* gde
   cudaStream_t st = (cudaStream_t)stream;
   int vec = pick_vec(B, H, W, {gP, gdepth});
   const int ipp = H * W / vec;
-  if (vec == 4) unproject_bwd_kernel<4><<<grid_for(unproject_bwd_kernel<4>, B, ipp), kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
-  else if (vec == 2) unproject_bwd_kernel<2><<<grid_for(unproject_bwd_kernel<2>, B, ipp), kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
-  else unproject_bwd_kernel<1><<<grid_for(unproject_bwd_kernel<1>, B, ipp), kThreads, 0, st>>>(gP, poses, gdepth, H, W, which);
+  if (vec == 4) dvd::launch(unproject_bwd_kernel<4>, grid_for(unproject_bwd_kernel<4>, B, ipp), kThreads, 0, st, gP, poses, gdepth, H, W, which);
+  else if (vec == 2) dvd::launch(unproject_bwd_kernel<2>, grid_for(unproject_bwd_kernel<2>, B, ipp), kThreads, 0, st, gP, poses, gdepth, H, W, which);
+  else dvd::launch(unproject_bwd_kernel<1>, grid_for(unproject_bwd_kernel<1>, B, ipp), kThreads, 0, st, gP, poses, gdepth, H, W, which);
   DVD_CUDA_LAUNCH_CHECK("unproject_bwd");
   return 0;
 }
@@ -1383,12 +1393,12 @@ extern "C" int dvd_reproject_loss_fwd(const float* depth_1, const float* depth_2
     if (vec == 4) g = grid_for(reproject_loss_fwd_kernel<4, 3>, B, ipp);
     else if (vec == 2) g = grid_for(reproject_loss_fwd_kernel<2, 4>, B, ipp);
     else g = grid_for(reproject_loss_fwd_kernel<1, 4>, B, ipp);
-    if (vec == 4) reproject_loss_fwd_kernel<4, 3><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
-    else if (vec == 2) reproject_loss_fwd_kernel<2, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
-    else reproject_loss_fwd_kernel<1, 4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+    if (vec == 4) dvd::launch(reproject_loss_fwd_kernel<4, 3>, g, kThreads, 0, st, depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+    else if (vec == 2) dvd::launch(reproject_loss_fwd_kernel<2, 4>, g, kThreads, 0, st, depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
+    else dvd::launch(reproject_loss_fwd_kernel<1, 4>, g, kThreads, 0, st, depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, partials, H, W);
   }
   DVD_CUDA_LAUNCH_CHECK("reproject_loss_fwd");
-  reproject_finalize_kernel<<<1, 256, 0, st>>>(partials, (int)(g.x * g.y), *cfg, scalars);
+  dvd::launch(reproject_finalize_kernel, 1, 256, 0, st, partials, (int)(g.x * g.y), *cfg, scalars);
   DVD_CUDA_LAUNCH_CHECK("reproject_finalize");
   return 0;
 }
@@ -1436,9 +1446,9 @@ extern "C" int dvd_reproject_loss_bwd(const float* depth_1, const float* depth_2
   const int ipp = H * W / vec;
   dim3 g = vec == 4 ? grid_for(reproject_loss_bwd_kernel<4>, B, ipp)
                     : (vec == 2 ? grid_for(reproject_loss_bwd_kernel<2>, B, ipp) : grid_for(reproject_loss_bwd_kernel<1>, B, ipp));
-  if (vec == 4) reproject_loss_bwd_kernel<4><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
-  else if (vec == 2) reproject_loss_bwd_kernel<2><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
-  else reproject_loss_bwd_kernel<1><<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
+  if (vec == 4) dvd::launch(reproject_loss_bwd_kernel<4>, g, kThreads, 0, st, depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
+  else if (vec == 2) dvd::launch(reproject_loss_bwd_kernel<2>, g, kThreads, 0, st, depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
+  else dvd::launch(reproject_loss_bwd_kernel<1>, g, kThreads, 0, st, depth_1, depth_2, flow_1_2, mask_2, sf, poses, *cfg, scalars, gscale, gscale_dev, g_sf, g_depth_2, H, W);
   DVD_CUDA_LAUNCH_CHECK("reproject_loss_bwd");
   return 0;
 }
@@ -1452,7 +1462,7 @@ extern "C" int dvd_reproject_materialize(const float* depth_1, const float* dept
   DVD_ARG_CHECK(depth_1 && depth_2 && flow_1_2 && poses, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g = grid_for(reproject_materialize_kernel, B, H * W);
-  reproject_materialize_kernel<<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, sf, poses, global_p1, sf_by_depth,
+  dvd::launch(reproject_materialize_kernel, g, kThreads, 0, st, depth_1, depth_2, flow_1_2, sf, poses, global_p1, sf_by_depth,
                                                        warped_global_p2, warped_p2_camera_2, p1_camera_2, dflow_1_2,
                                                        staticflow_1_2, depth_image_1_2, depth_warp_1_2, H, W);
   DVD_CUDA_LAUNCH_CHECK("reproject_materialize");
@@ -1474,7 +1484,7 @@ extern "C" int dvd_reproject_materialize_bwd(const float* depth_1, const float* 
   MatGrads G{g_global_p1, g_sf_by_depth, g_warped_global_p2, g_warped_p2_camera_2, g_p1_camera_2,
              g_dflow_1_2, g_staticflow_1_2, g_depth_image_1_2, g_depth_warp_1_2};
   dim3 g = grid_for(reproject_materialize_bwd_kernel, B, H * W);
-  reproject_materialize_bwd_kernel<<<g, kThreads, 0, st>>>(depth_1, depth_2, flow_1_2, sf, poses, G, g_depth_1, g_depth_2,
+  dvd::launch(reproject_materialize_bwd_kernel, g, kThreads, 0, st, depth_1, depth_2, flow_1_2, sf, poses, G, g_depth_1, g_depth_2,
                                                          g_sf, H, W);
   DVD_CUDA_LAUNCH_CHECK("reproject_materialize_bwd");
   return 0;

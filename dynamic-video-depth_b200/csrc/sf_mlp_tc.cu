@@ -46,6 +46,7 @@ struct PackParams {
 };
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(PackParams P) {
+  DVD_PDL_ENTER();
   const int img = blockIdx.y / kLayers, l = blockIdx.y % kLayers;
   const int in = layer_in(P.L, l), out = layer_out(l);
   const float* __restrict__ W = P.w[l];
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_chain_fwd_kernel(const __g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const MlpLayout& L = P.L;
   chain_setup(S, warp, lane);
+  DVD_PDL_ENTER();               // barriers / tensor memory are set up: now wait for the producer of the operands
   for (int i = threadIdx.x; i < 5 * 256 + 16; i += blockDim.x) S.bias[i] = P.bias[i];
   tc_fence_before();
   __syncthreads();
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(kThreadsMlp, 1) mlp_dgrad_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = *S.tmem_holder;
   const long ntiles = L.ntiles;
+  DVD_PDL_ENTER();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -704,6 +707,7 @@ __global__ void __launch_bounds__(kThreadsWgrad, 1) mlp_wgrad_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
   const bool have_work = q1 > q0;
+  DVD_PDL_ENTER();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -792,6 +796,7 @@ __global__ void __launch_bounds__(kThreadsWgrad, 1) mlp_wgrad_kernel(const __gri
 __global__ void __launch_bounds__(256) acc_reg_kernel(const float* __restrict__ s0, const float* __restrict__ s1, float c,
                                                       float* __restrict__ g0, float* __restrict__ g1,
                                                       float* __restrict__ partials, long n) {
+  DVD_PDL_ENTER();
   __shared__ float red[8];
   float acc = 0.f;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -812,6 +817,7 @@ __global__ void __launch_bounds__(256) acc_reg_kernel(const float* __restrict__ 
 }
 __global__ void __launch_bounds__(256) acc_reg_final_kernel(const float* __restrict__ partials, int nb, float scale,
                                                             float* __restrict__ out) {
+  DVD_PDL_ENTER();
   __shared__ double red[8];
   double a = 0;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) a += partials[i];
@@ -873,7 +879,7 @@ extern "C" int dvd_mlp_pack_weights(const dvd_mlp_cfg* cfg, const float* const* 
   P.wf = (uint8_t*)packed_fwd;
   P.wb = (uint8_t*)packed_bwd;
   P.L = make_layout(*cfg, 128);
-  pack_weights_kernel<<<dim3(32, 2 * kLayers), 256, 0, (cudaStream_t)stream>>>(P);
+  dvd::launch(pack_weights_kernel, dim3(32, 2 * kLayers), 256, 0, (cudaStream_t)stream, P);
   DVD_CUDA_LAUNCH_CHECK("mlp_pack_weights");
   return 0;
 }
@@ -884,11 +890,11 @@ static int launch_fwd(const FwdParams& P, bool save, cudaStream_t st) {
   if (save) {
     DVD_CUDA_CALL(cudaFuncSetAttribute(mlp_chain_fwd_kernel<FX, FT, TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kChainSmemBytes));
-    mlp_chain_fwd_kernel<FX, FT, TD, true><<<grid, kThreadsMlp, kChainSmemBytes, st>>>(P);
+    dvd::launch(mlp_chain_fwd_kernel<FX, FT, TD, true>, grid, kThreadsMlp, kChainSmemBytes, st, P);
   } else {
     DVD_CUDA_CALL(cudaFuncSetAttribute(mlp_chain_fwd_kernel<FX, FT, TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kChainSmemBytes));
-    mlp_chain_fwd_kernel<FX, FT, TD, false><<<grid, kThreadsMlp, kChainSmemBytes, st>>>(P);
+    dvd::launch(mlp_chain_fwd_kernel<FX, FT, TD, false>, grid, kThreadsMlp, kChainSmemBytes, st, P);
   }
   DVD_CUDA_LAUNCH_CHECK("mlp_chain_fwd");
   return 0;
@@ -933,11 +939,11 @@ extern "C" int dvd_mlp_dgrad(const dvd_mlp_cfg* cfg, const void* packed_bwd, con
   if (variant == 0) {
     DVD_CUDA_CALL(cudaFuncSetAttribute(mlp_dgrad_kernel<16, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kChainSmemBytes));
-    mlp_dgrad_kernel<16, 16, true><<<grid, kThreadsMlp, kChainSmemBytes, st>>>(P);
+    dvd::launch(mlp_dgrad_kernel<16, 16, true>, grid, kThreadsMlp, kChainSmemBytes, st, P);
   } else {
     DVD_CUDA_CALL(cudaFuncSetAttribute(mlp_dgrad_kernel<16, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kChainSmemBytes));
-    mlp_dgrad_kernel<16, 0, false><<<grid, kThreadsMlp, kChainSmemBytes, st>>>(P);
+    dvd::launch(mlp_dgrad_kernel<16, 0, false>, grid, kThreadsMlp, kChainSmemBytes, st, P);
   }
   DVD_CUDA_LAUNCH_CHECK("mlp_dgrad");
   return 0;
@@ -978,7 +984,7 @@ extern "C" int dvd_mlp_wgrad(const dvd_mlp_cfg* cfg, const void* save_e, const v
   if (ksplit < 1) ksplit = 1;
   if ((long)ksplit > L.nq) ksplit = (int)L.nq;
   DVD_CUDA_CALL(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmemBytes));
-  mlp_wgrad_kernel<<<dim3(nj, ksplit), kThreadsWgrad, kWgradSmemBytes, (cudaStream_t)stream>>>(P);
+  dvd::launch(mlp_wgrad_kernel, dim3(nj, ksplit), kThreadsWgrad, kWgradSmemBytes, (cudaStream_t)stream, P);
   DVD_CUDA_LAUNCH_CHECK("mlp_wgrad");
   return 0;
 }
@@ -989,9 +995,9 @@ extern "C" int dvd_acc_reg(const float* s0, const float* s1, float acc_mul, floa
   const float inv = 1.0f / ((float)numel + 1e-6f);
   int nb = (int)((numel + 255) / 256);
   if (nb > 1024) nb = 1024;
-  acc_reg_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(s0, s1, acc_mul * inv * gscale, g_s0, g_s1, partials, numel);
+  dvd::launch(acc_reg_kernel, nb, 256, 0, (cudaStream_t)stream, s0, s1, acc_mul * inv * gscale, g_s0, g_s1, partials, numel);
   DVD_CUDA_LAUNCH_CHECK("acc_reg");
-  acc_reg_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, nb, acc_mul * inv, loss_out);
+  dvd::launch(acc_reg_final_kernel, 1, 256, 0, (cudaStream_t)stream, partials, nb, acc_mul * inv, loss_out);
   DVD_CUDA_LAUNCH_CHECK("acc_reg_final");
   return 0;
 }

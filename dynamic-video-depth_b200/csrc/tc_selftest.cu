@@ -10,6 +10,7 @@ using namespace tc;
 // mode 0: A from shared memory (SS), mode 1: A from tensor memory (TS). passes: 1 (bf16) or 3 (bf16x3)
 __global__ void __launch_bounds__(160, 1) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                                float* __restrict__ D, int K, int N, int mode, int passes) {
+  DVD_PDL_ENTER();
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must start on 1024-byte boundaries of the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -165,7 +166,7 @@ extern "C" int dvd_selftest_umma(const float* A, const float* B, float* D, int K
   DVD_ARG_CHECK(passes == 1 || passes == 3, "passes 1 or 3");
   size_t smem = (size_t)(K / 64) * 2 * (128 * 128 + (size_t)((N + 63) / 64) * 8192) + 1024;
   DVD_CUDA_CALL(cudaFuncSetAttribute(dvd::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dvd::umma_selftest_kernel<<<1, 160, smem, (cudaStream_t)stream>>>(A, B, D, K, N, mode, passes);
+  dvd::launch(dvd::umma_selftest_kernel, 1, 160, smem, (cudaStream_t)stream, A, B, D, K, N, mode, passes);
   DVD_CUDA_LAUNCH_CHECK("umma_selftest");
   return 0;
 }

@@ -58,14 +58,16 @@ class MidasEngine:
         self._all = [c for st in self.stages for b in st for c in b.convs()] + self.rn
         self._all += [c for r in self.rcu_a[:3] + self.rcu_b for c in (r.c1, r.c2)] + [self.oc0, self.oc2]
         self.saved = None
+        self._table = None
         # called as grad_hook(stage) at the points of backward() where a contiguous block of parameter gradients is final:
         # 'decoder+layer4', 'layer3', 'rest' - the data-parallel path all-reduces that block while the backward goes on
         self.grad_hook = None
 
     # ---------------------------------------------------------------------------------------------------
     def pack(self, need_bwd=True):
-        for c in self._all:
-            c.pack(need_bwd)
+        if self._table is None:
+            self._table = co.PackTable(self._all)
+        self._table.pack(need_bwd)
 
     def _ensure_grads(self):
         for p in self.net.parameters():

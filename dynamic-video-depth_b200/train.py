@@ -41,6 +41,11 @@ def main_worker(local_rank, ngpus, opt):
         torch.manual_seed(opt.manual_seed + rank)
     logger = NullLogger()
     model = get_model(opt.net)(opt, logger)
+    if opt.dataset == 'synthetic_sequence' and opt.resume == 0 and getattr(opt, 'midas', False):
+        # no pretrained MiDaS checkpoint ships with the synthetic sequence: with default-initialised weights 10000 / out leaves the
+        # valid depth range and every loss is identically zero - use the seeded synthetic weights of the benchmark
+        from . import synthetic
+        synthetic.seed_net_(model.net_depth, opt.manual_seed or 0, 2000.0)
     Dataset = get_dataset(opt.dataset)
     ds = Dataset(opt, mode='train', model=model)
     initial_epoch = 1

@@ -224,6 +224,15 @@ int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const float* w_im
                     const float* bn_beta, const float* bn_mean, const float* bn_var, const float* res, const float* res2,
                     const float* mask, float* y, void* stream);
 
+/* The same with an exchange area for the stream-K schedule (layers whose tile count leaves much of the last wave idle are cut
+ * into equal K ranges per SM; tiles shared by several SMs are summed through this area). `workspace`: at least
+ * dvd_conv2d_workspace_bytes() bytes of device memory, 16-byte aligned, ZEROED ONCE by the caller and then left to the library;
+ * launches that share a workspace must be ordered on one stream. NULL = whole tiles only (dvd_conv2d_nhwc).                  */
+size_t dvd_conv2d_workspace_bytes(void);
+int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, const float* w_img, const float* bias, const float* bn_gamma,
+                       const float* bn_beta, const float* bn_mean, const float* bn_var, const float* res, const float* res2,
+                       const float* mask, float* y, void* workspace, size_t workspace_bytes, void* stream);
+
 /* weight[co, ci_local, ky, kx] (element strides given; groups of Cin/groups in-channels) -> TF32-rounded image
  *   w_fwd: forward        [k*k][Cout][Cin or kblock]
  *   w_bwd: data gradient  [k*k][Cin][Cout or kblock], multiplied by gamma*rsqrt(var+eps) of the out-channel when given
@@ -232,6 +241,23 @@ int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const float* w_im
 int dvd_conv2d_pack(const float* weight, long stride_co, long stride_ci, long stride_ky, long stride_kx, float* w_fwd,
                     float* w_bwd, int Cout, int Cin, int ksize, int groups, int kblock, const float* bn_gamma,
                     const float* bn_var, float bn_eps, void* stream);
+
+/* The same for every layer of a net in ONE launch. `items_dev` is a table of n_items entries in DEVICE memory (the pointers in
+ * it are device pointers; the caller rebuilds it when a tensor moves). Entry i owns grid blocks [blk0, blk0 + blocks_i) with
+ * blocks_i = dvd_conv2d_pack_blocks(...) and blk0 the running sum; total_blocks = the sum over all entries.                    */
+typedef struct dvd_pack_item {
+  const float* weight;      /* [Cout, Cin/groups, k, k], element strides below */
+  float* w_fwd;             /* forward image or NULL */
+  float* w_bwd;             /* data-gradient image or NULL (skipped when want_bwd == 0) */
+  const float* bn_gamma;    /* eval-BatchNorm scale folded into w_bwd, or NULL */
+  const float* bn_var;
+  long s_co, s_ci, s_ky, s_kx;
+  long blk0;
+  int Cout, Cin, ksize, groups, kblock;
+  float bn_eps;
+} dvd_pack_item;
+long dvd_conv2d_pack_blocks(int Cout, int Cin, int ksize, int groups, int kblock);
+int dvd_conv2d_pack_batch(const dvd_pack_item* items_dev, int n_items, long total_blocks, int want_bwd, void* stream);
 
 /* dweight[co, ci_local, ky, kx] += sc[co] * sum_px gy[px, co] * x[stride*px + (dy,dx)(tap), ci]   (fp32 reductions, any strides)
  * for the taps of `desc` (wt[t] = ky*ksize + kx). With an eval-mode BatchNorm behind the convolution, gy is the UN-scaled

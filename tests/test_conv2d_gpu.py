@@ -75,6 +75,10 @@ FWD_CASES = [
     (1, 7, 12, 2048, 2048, 3, 1, 32, True, False, False, False, True, False),  # 64 ch / group
     (2, 56, 96, 512, 512, 3, 2, 32, True, False, False, False, True, False),   # grouped + stride 2 (layer2.0.conv2)
     (1, 27, 45, 256, 256, 3, 2, 32, True, False, False, False, True, False),   # grouped + stride 2, odd sizes
+    (16, 14, 24, 1024, 1024, 1, 1, 1, True, False, True, False, True, False),  # layer3 1x1 at the bench batch: 84 pair tiles on 74 pairs
+    (16, 7, 12, 2048, 256, 3, 1, 1, False, True, False, False, True, False),   # layer4_rn at the bench batch: 6 pair tiles, 576 K-steps -> stream-K
+    (16, 14, 24, 1024, 256, 3, 1, 1, False, True, True, True, True, False),    # layer3_rn class: 24 pair tiles, 288 K-steps -> stream-K, + residuals
+    (2, 14, 24, 256, 256, 3, 1, 1, False, True, True, True, True, False),      # few tiles, 72 K-steps: tiles split four ways
     (1, 20, 36, 64, 64, 5, 1, 1, False, True, False, False, True, False),      # 5x5 (hourglass class): 25 taps
     (1, 24, 40, 32, 32, 11, 1, 1, False, True, False, False, True, False),     # 11x11: 121 taps
 ]
@@ -119,6 +123,48 @@ def test_conv_forward_matches_torch_fp64(case):
     if not has_mask:
         y2 = c.fwd(cl(x), res=cl(res) if has_res else None, res2=cl(res2) if has_res2 else None, relu=relu, round_out=True)
         assert torch.equal(y2, co.round_tf32(y))
+
+
+def test_stream_k_schedule_matches_whole_tiles_and_leaves_flags_clear():
+    """Same launch with and without the stream-K schedule (DVD_CONV_STREAMK=0 = whole tiles): equal up to fp32 summation order;
+    the flag words of the exchange area are back to zero afterwards (the next launch relies on it); launches of OTHER shapes in
+    between (other tile widths, cluster counts) must not disturb it (stale lines of the exchange area in an SM's L1 did, once)."""
+    import os
+    from dvd_b200 import conv_ops as co
+    g = gen(77)
+
+    def layer(ci, co_, k, N, H, W, seed):
+        conv = make_conv(ci, co_, k, 1, 1, True, seed).cuda()
+        c = co.Conv(conv, None)
+        c.pack(need_bwd=False)
+        return c, cl(tf32(torch.randn(N, ci, H, W, generator=g)))
+
+    layers = [layer(2048, 256, 3, 16, 7, 12, 78), layer(1024, 256, 3, 16, 14, 24, 79), layer(64, 64, 5, 1, 20, 36, 80),
+              layer(512, 256, 3, 2, 14, 24, 81)]
+    ws = co.conv_workspace(layers[0][1].device)
+    assert ws is not None
+    ws[256:].zero_()
+    ref = []
+    os.environ['DVD_CONV_STREAMK'] = '0'
+    try:
+        for c, x in layers:
+            ref.append(c.fwd(x, relu=True, round_out=False))
+        torch.cuda.synchronize()
+        assert float(ws[256:].abs().max()) == 0.0
+    finally:
+        del os.environ['DVD_CONV_STREAMK']
+    first = None
+    for rep in range(3):
+        outs = [c.fwd(x, relu=True, round_out=False) for c, x in layers]
+        torch.cuda.synchronize()
+        assert int((ws[:256].view(torch.int32) != 0).sum()) == 0
+        for y, r in zip(outs, ref):
+            assert rel_err(y, r) < 4 * TOL       # two fp32 summation orders of up to 18 432 products against each other
+        if first is None:
+            first = outs
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(outs, first))      # the schedule is deterministic
+    assert float(ws[256:].abs().max()) > 0, 'these shapes are expected to take the stream-K schedule'
 
 
 DGRAD_CASES = [
