@@ -373,7 +373,11 @@ def roofline_depth_convs(model, batch, epoch, tflops_peak, peak_kind):
     from dvd_b200 import conv_ops
     conv_ops.PROFILE = []
     graph_flag = getattr(model.opt, 'cuda_graph', True)
-    model.opt.cuda_graph = False          # the probe brackets individual launches: run this one step eagerly
+    model.opt.cuda_graph = False          # the probe brackets individual launches: run this one step eagerly,
+    world_flag = model._world             # on this rank alone (the other ranks have left: no gradient exchange),
+    model._world = 1
+    overlap_flag = os.environ.get('DVD_BWD_OVERLAP')
+    os.environ['DVD_BWD_OVERLAP'] = '0'   # and on one stream (concurrent launches would be billed each other's time)
     try:
         model._train_on_batch(epoch, 0, batch)
         torch.cuda.synchronize()
@@ -381,6 +385,11 @@ def roofline_depth_convs(model, batch, epoch, tflops_peak, peak_kind):
     finally:
         conv_ops.PROFILE = None
         model.opt.cuda_graph = graph_flag
+        model._world = world_flag
+        if overlap_flag is None:
+            del os.environ['DVD_BWD_OVERLAP']
+        else:
+            os.environ['DVD_BWD_OVERLAP'] = overlap_flag
     agg = {}
     for kind, flops, e0, e1, _info in rec:
         a = agg.setdefault(kind, [0.0, 0.0, 0])
@@ -498,6 +507,7 @@ def run_b200_arm(args):
         del host1, res1
     if rank != 0:
         if world > 1:
+            model.release_graphs()      # NCCL cannot destroy a communicator while graphs that captured its collectives are alive
             dist.destroy_process_group()
         return
     hbm_peak, tflops_peak, peak_kind = measured_peaks()
@@ -544,6 +554,7 @@ def run_b200_arm(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        model.release_graphs()
         dist.destroy_process_group()
 
 

@@ -61,6 +61,7 @@ SIGNATURES = {
     'dvd_reproject_materialize': [_P] * 14 + [_I, _I, _I, _P],
     'dvd_reproject_materialize_bwd': [_P] * 17 + [_I, _I, _I, _P],
     'dvd_selftest_umma': [_P, _P, _P, _I, _I, _I, _I, _P],
+    'dvd_selftest_halo': [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     'dvd_mlp_packed_weights_bytes': [ctypes.POINTER(MlpCfg)],
     'dvd_mlp_save_bytes_per_eval': [ctypes.POINTER(MlpCfg), ctypes.c_long],
     'dvd_mlp_dy_bytes': [ctypes.POINTER(MlpCfg), ctypes.c_long],

@@ -329,7 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
   const uint16_t cmask = (uint16_t)((1u << P.csize) - 1u);
   const int m_tiles = P.d.N * P.tiles_w * P.tiles_h;
   const int mgroups = (m_tiles + P.csize - 1) / P.csize;
-  const int n_tiles = P.d.Cout / P.NT;
+  const int n_tiles = (P.d.Cout + P.NT - 1) / P.NT;   // the last channel tile may be ragged (whole 32-channel blocks): the weight
+                                                      // rows beyond Cout are zero-filled by the TMA unit, the epilogue skips them
   const int ntiles = mgroups * n_tiles;           // cluster tiles
   const int ksteps = P.d.ntaps * P.kchunks;
   const uint32_t stage_tx = (uint32_t)kABytes + (uint32_t)P.NT * 128u;
@@ -469,14 +470,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
       const float* mrow = (P.mask && valid) ? P.mask + off : nullptr;
       float* yrow = P.y + off;
       if (P.tma_store) {
+        const int ntv = min(P.NT, P.d.Cout - T.n0);      // channels of this tile that exist (ragged last tile)
         // residual / mask of this warp's first block: in flight while the MMAs of the tile are still running
         float4 resv[8], maskv[8];
-        if (rrow) load_row<8>(rrow + hsel * 32, resv);
-        if (mrow) load_row<8>(mrow + hsel * 32, maskv);
+        if (rrow && hsel * 32 < ntv) load_row<8>(rrow + hsel * 32, resv);
+        if (mrow && hsel * 32 < ntv) load_row<8>(mrow + hsel * 32, maskv);
         if (has_aff) {
           // fold BatchNorm / bias of this tile's channels once: y = acc * scale + shift
           asm volatile("bar.sync 2, 256;" ::: "memory");      // previous tile's readers are done
-          for (int i = et; i < P.NT; i += 256) {
+          for (int i = et; i < ntv; i += 256) {
             const int c = T.n0 + i;
             float sc = 1.f, sh = 0.f;
             if (P.gamma) {
@@ -541,14 +543,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
         }
         const uint32_t d = tmem + buf * (uint32_t)kMaxNT + lane_base;
         const int bh0 = T.h0 + (q * 32) / P.TW, bw0 = T.w0 + (q * 32) % P.TW;
-        for (int c0 = hsel * 32; c0 < P.NT; c0 += 64) {
+        for (int c0 = hsel * 32; c0 < ntv; c0 += 64) {
           uint32_t r[32];
           tmem_ld32(d + c0, r);
           tmem_ld_wait();
-          if (c0 + 64 >= P.NT) release_acc(buf);  // this warp has read its share of the accumulator
+          if (c0 + 64 >= ntv) release_acc(buf);   // this warp has read its share of the accumulator
           epilogue_math<32>(P, r, has_aff ? aff_mem + c0 : nullptr, rrow ? resv : nullptr, r2row ? r2row + c0 : nullptr,
                             mrow ? maskv : nullptr);
-          if (c0 + 64 < P.NT) {                   // next block's residual / mask: in flight during the staging / store below
+          if (c0 + 64 < ntv) {                    // next block's residual / mask: in flight during the staging / store below
             if (rrow) load_row<8>(rrow + c0 + 64, resv);
             if (mrow) load_row<8>(mrow + c0 + 64, maskv);
           }
@@ -564,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
             bulk_commit();
           }
         }
-        if (hsel * 32 >= P.NT) release_acc(buf);  // NT = 32: the odd warps have no block, but owe their arrival
+        if (hsel * 32 >= ntv) release_acc(buf);   // 32 channels: the odd warps have no block, but owe their arrival
         if (n_part) {
           // every reader is done with the partial tiles: lower the flags for the next launch (ordered by the kernel boundary)
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -1094,7 +1096,6 @@ extern "C" int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, con
   P.bias = bias; P.gamma = bn_gamma; P.beta = bn_beta; P.mean = bn_mean; P.var = bn_var;
   P.res = res; P.res2 = res2; P.mask = mask; P.y = y;
   P.NT = d.kblock ? d.kblock : (d.Cout >= kMaxNT ? kMaxNT : d.Cout);
-  if (d.Cout % P.NT != 0) { set_error("dvd_conv2d_nhwc: Cout=%d is not a multiple of the %d-channel tile", d.Cout, P.NT); return -2; }
   P.kchunks = (d.kblock ? d.kblock : d.Cin) / 32;
   const bool identity_out = d.oy_mul == 1 && d.ox_mul == 1 && d.oy_add == 0 && d.ox_add == 0 && d.YH == d.OH && d.YW == d.OW;
   const bool pointwise = d.ntaps == 1 && d.dy[0] == 0 && d.dx[0] == 0 && d.stride == 1 && identity_out && d.H == d.OH && d.W == d.OW;
@@ -1137,6 +1138,30 @@ extern "C" int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, con
     const char* ev = getenv("DVD_CONV_PAIR");
     P.pair = (ev && atoi(ev) == 0) ? 0 : 1;
   }
+  const long full = max_clusters(conv2d_tc_kernel<false>, kThreads, kSmem, P.csize);
+  const long mgroups_h = (m_tiles_h + P.csize - 1) / P.csize;
+  // Channel-tile width. 256 is the most efficient tile, but whole tiles come in waves: 84 tiles on 74 CTA pairs (the 45 1x1
+  // layers of ResNeXt's layer3 at 16 images) take two rounds of which the second is 14 % full. A narrower tile that fills the
+  // rounds wins when  rounds(NT) * t(NT)  is smaller, t(NT) = 0.47 + 0.53 * NT / 256 the measured relative cost of a K-step
+  // (profiles/r2_conv_table: 3x3 256->256 at NT 256 vs 256->128 at NT 128). Dense layers with a TMA-store epilogue only; the
+  // last tile may be ragged in whole 32-channel blocks.
+  if (!d.kblock && P.tma_store && d.Cout > kMaxNT && d.Cout % 32 == 0) {
+    const char* ev = getenv("DVD_CONV_NT");
+    if (ev && atoi(ev) >= 32 && atoi(ev) <= kMaxNT && atoi(ev) % 32 == 0) {
+      P.NT = atoi(ev);
+    } else if (!(ev && atoi(ev) == 0)) {
+      double best = 1e30;
+      for (int nt = kMaxNT; nt >= 128; nt -= 32) {
+        const long tiles = mgroups_h * ((d.Cout + nt - 1) / nt);
+        const double cost = (double)((tiles + full - 1) / full) * (0.47 + 0.53 * nt / 256.0);
+        if (cost < best * 0.97) { best = cost; P.NT = nt; }      // a narrower tile must win by 3 %
+      }
+    }
+  }
+  if (d.Cout % P.NT != 0 && !(P.tma_store && d.Cout % 32 == 0 && !d.kblock)) {
+    set_error("dvd_conv2d_nhwc: Cout=%d is not a multiple of the %d-channel tile", d.Cout, P.NT);
+    return -2;
+  }
   CUtensorMap mapA, mapW, mapY;
   if (int e = make_nhwc_map(&mapA, x, inN, inH, inW, d.Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   {
@@ -1154,8 +1179,7 @@ extern "C" int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, con
   } else {
     mapY = mapA;
   }
-  const long ctiles = ((m_tiles_h + P.csize - 1) / P.csize) * (d.Cout / P.NT);      // cluster tiles
-  const long full = max_clusters(conv2d_tc_kernel<false>, kThreads, kSmem, P.csize);
+  const long ctiles = mgroups_h * ((d.Cout + P.NT - 1) / P.NT);      // cluster tiles
   long nclusters = ctiles < full ? ctiles : full;
   // stream-K when whole tiles would leave a large part of the machine idle in the last (or only) wave: cut the (tile, K-step)
   // list into equal contiguous ranges instead. Needs the caller's exchange area (zeroed once; the kernel leaves it zeroed where

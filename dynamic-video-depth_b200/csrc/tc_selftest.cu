@@ -154,6 +154,83 @@ __global__ void __launch_bounds__(160, 1) umma_selftest_kernel(const float* __re
   }
 }
 
+// Probe for halo-resident convolution tiles: A is an image of R pixel rows x 32 fp32 channels in the K-major SWIZZLE_128B layout
+// (row r at byte r * 128 from a 1024-aligned base, 16-byte chunk c stored at c ^ (r & 7) - exactly what a TMA box {32 ch, W, H}
+// writes). The MMA reads 128 of those rows through a descriptor whose START is shifted by `shift` rows (not a multiple of 8) and
+// whose 8-row groups are `sbo_rows` rows apart: D[m][n] = sum_k A[shift + (m / 8) * sbo_rows + m % 8][k] * B[n][k]  (TF32).
+// bo_mode 1 additionally writes (start >> 7) & 7 into the descriptor's base-offset field (bits 49-51).
+__global__ void __launch_bounds__(160, 1) halo_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                               float* __restrict__ D, int R, int N, int shift, int sbo_rows, int bo_mode) {
+  DVD_PDL_ENTER();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_holder;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)((R * 128 + 1023) / 1024) * 1024;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 4) {
+    tmem_alloc(&tmem_base_holder, 256);
+    if (lane == 0) {
+      mbar_init(&bar_done, 1);
+      fence_mbar_init();
+    }
+  }
+  for (int i = threadIdx.x; i < R * 8; i += blockDim.x) {
+    const int r = i / 8, c = i % 8;
+    *reinterpret_cast<float4*>(sA + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const float4*>(A + r * 32 + c * 4);
+  }
+  for (int i = threadIdx.x; i < N * 8; i += blockDim.x) {
+    const int r = i / 8, c = i % 8;
+    *reinterpret_cast<float4*>(sB + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const float4*>(B + r * 32 + c * 4);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_holder;
+  if (warp == 4 && lane == 0) {
+    // kind::tf32, M = 128, both operands K-major
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t a_addr = smem_u32(sA) + (uint32_t)shift * 128u + ks * 32;
+      uint64_t ad = 0;
+      ad |= (uint64_t)((a_addr >> 4) & 0x3FFF);
+      ad |= (uint64_t)((((uint32_t)sbo_rows * 128u) >> 4) & 0x3FFF) << 32;
+      ad |= (uint64_t)1 << 46;
+      if (bo_mode == 1) ad |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+      ad |= (uint64_t)2 << 61;
+      const uint64_t bd = make_sdesc_k_sw128(smem_u32(sB) + ks * 32);
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem),
+          "l"(ad), "l"(bd), "r"(idesc), "r"(ks ? 1u : 0u)
+          : "memory");
+    }
+    umma_commit(&bar_done);
+  }
+  if (warp < 4) {
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem + lane_base + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) D[row * N + c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 }  // namespace dvd
 
 // A [128,K] fp32 row-major, B [N,K] fp32 row-major, D [128,N] fp32; K in {64,128}, N in {16..256, %16}
@@ -168,5 +245,18 @@ extern "C" int dvd_selftest_umma(const float* A, const float* B, float* D, int K
   DVD_CUDA_CALL(cudaFuncSetAttribute(dvd::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dvd::launch(dvd::umma_selftest_kernel, 1, 160, smem, (cudaStream_t)stream, A, B, D, K, N, mode, passes);
   DVD_CUDA_LAUNCH_CHECK("umma_selftest");
+  return 0;
+}
+
+// A [R,32] fp32 (TF32 values), B [N,32], D [128,N]; see halo_selftest_kernel
+extern "C" int dvd_selftest_halo(const float* A, const float* B, float* D, int R, int N, int shift, int sbo_rows, int bo_mode,
+                                 void* stream) {
+  DVD_ARG_CHECK(A && B && D, "null pointer");
+  DVD_ARG_CHECK(N >= 16 && N <= 256 && N % 16 == 0 && R >= 128 && R <= 1024, "bad sizes");
+  DVD_ARG_CHECK(shift >= 0 && sbo_rows >= 8 && shift + 15 * sbo_rows + 8 <= R, "rows out of range");
+  size_t smem = (size_t)((R * 128 + 1023) / 1024) * 1024 + (size_t)N * 128 + 2048;
+  DVD_CUDA_CALL(cudaFuncSetAttribute(dvd::halo_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dvd::launch(dvd::halo_selftest_kernel, 1, 160, smem, (cudaStream_t)stream, A, B, D, R, N, shift, sbo_rows, bo_mode);
+  DVD_CUDA_LAUNCH_CHECK("halo_selftest");
   return 0;
 }

@@ -18,6 +18,8 @@ Parameter gradients are ACCUMULATED into `p.grad` (the flat gradient buffer of d
 otherwise) — the engine is the owner of the depth net's backward, autograd only sees one node (`MidasFunction`).
 Activations handed between convolutions are stored TF32-rounded (rounded-operand contract, conv_ops.py).
 """
+import os
+
 import torch
 
 from . import conv_ops as co
@@ -59,9 +61,47 @@ class MidasEngine:
         self._all += [c for r in self.rcu_a[:3] + self.rcu_b for c in (r.c1, r.c2)] + [self.oc0, self.oc2]
         self.saved = None
         self._table = None
+        self._side, self._keep, self._side_streams = None, [], {}
         # called as grad_hook(stage) at the points of backward() where a contiguous block of parameter gradients is final:
         # 'decoder+layer4', 'layer3', 'rest' - the data-parallel path all-reduces that block while the backward goes on
         self.grad_hook = None
+
+    # ---------------------------------------------------------------------------------------------------
+    # Two-stream backward. The weight gradient of a layer depends only on tensors the data-gradient chain has already produced
+    # (the layer's input activation and the masked gradient of its output): it is issued on a SIDE stream behind an event, while
+    # the main stream goes on with the data gradient. Both kernels are persistent one-CTA-per-SM grids, so the hardware fills the
+    # SMs a finishing grid leaves idle (its last, partly empty wave; launch latency; prologue) with CTAs of the other stream.
+    # Tensors handed to the side stream are kept alive until the next join (the caching allocator would otherwise hand their
+    # memory to the main stream while the side stream still reads it).
+    def _side_begin(self):
+        self._side = None
+        self._keep = []
+        if os.environ.get('DVD_BWD_OVERLAP', '1') == '0':
+            return
+        dev = torch.cuda.current_device()
+        st = self._side_streams.get(dev)
+        if st is None:
+            st = self._side_streams[dev] = torch.cuda.Stream(device=dev)
+        self._side = st
+
+    def _on_side(self, fn, *keep):
+        if self._side is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            fn()
+        self._keep.extend(keep)
+
+    def _side_join(self):
+        if self._side is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        torch.cuda.current_stream().wait_event(ev)
+        self._keep.clear()
 
     # ---------------------------------------------------------------------------------------------------
     def pack(self, need_bwd=True):
@@ -129,14 +169,15 @@ class MidasEngine:
             raise RuntimeError('MidasEngine.backward without a training forward')
         self.saved = None
         self._ensure_grads()
+        self._side_begin()
         g_depth = g_depth.contiguous()
         oc4 = self.oc4
         gm_h2 = co.head_bwd(S['h2'], oc4.weight, oc4.bias, g_depth, oc4.weight.grad, oc4.bias.grad, relu_mask=True)
         H1, W1 = S['h1'].shape[2:]
-        self.oc2.wgrad(S['h1'], gm_h2, sums=True)
+        self._on_side(lambda x_=S['h1'], g_=gm_h2: self.oc2.wgrad(x_, g_, sums=True), S['h1'], gm_h2)
         g_h1 = self.oc2.dgrad(gm_h2, H1, W1, round_out=False)
         g_h0 = co.upsample2x_bwd(g_h1, False)
-        self.oc0.wgrad(S['p1'], g_h0, sums=True)
+        self._on_side(lambda x_=S['p1'], g_=g_h0: self.oc0.wgrad(x_, g_, sums=True), S['p1'], g_h0)
         g_path = self.oc0.dgrad(g_h0, H1 // 2, W1 // 2, round_out=False)
         g_feat = [None] * 4
         for j, K in enumerate((0, 1, 2, 3)):      # refinenet1 .. refinenet4
@@ -145,20 +186,20 @@ class MidasEngine:
             g_o = co.upsample2x_bwd(g_path, True)
             Hk, Wk = g_o.shape[2:]
             rb = self.rcu_b[K]
-            rb.c2.wgrad(c1b, g_o, sums=True)
+            self._on_side(lambda x_=c1b, g_=g_o: rb.c2.wgrad(x_, g_, sums=True), c1b, g_o)
             g_c1b = rb.c2.dgrad(g_o, Hk, Wk, mask=c1b)
-            rb.c1.wgrad(t, g_c1b, sums=True)
+            self._on_side(lambda x_=t, g_=g_c1b: rb.c1.wgrad(x_, g_, sums=True), t, g_c1b)
             g_t = rb.c1.dgrad(g_c1b, Hk, Wk, res=g_o, mask=t)       # w.r.t. the pre-ReLU sum (t itself for refinenet4)
             if c1a is not None:
                 ra = self.rcu_a[K]
                 g_path = g_t                                         # the other fusion input: previous path
-                ra.c2.wgrad(c1a, g_t, sums=True)
+                self._on_side(lambda x_=c1a, g_=g_t: ra.c2.wgrad(x_, g_, sums=True), c1a, g_t)
                 g_c1a = ra.c2.dgrad(g_t, Hk, Wk, mask=c1a)
-                ra.c1.wgrad(lrK, g_c1a, sums=True)
+                self._on_side(lambda x_=lrK, g_=g_c1a: ra.c1.wgrad(x_, g_, sums=True), lrK, g_c1a)
                 g_lr = ra.c1.dgrad(g_c1a, Hk, Wk, res=g_t, mask=lrK)
             else:
                 g_lr = g_t
-            self.rn[K].wgrad(S['feats'][K], g_lr)
+            self._on_side(lambda x_=S['feats'][K], g_=g_lr: self.rn[K].wgrad(x_, g_), S['feats'][K], g_lr)
             g_feat[K] = self.rn[K].dgrad(g_lr, Hk, Wk, round_out=False)
         # encoder: gm3 = masked gradient w.r.t. the pre-ReLU output of the block being differentiated
         l4 = S['feats'][3]
@@ -173,27 +214,29 @@ class MidasEngine:
                 x_in, y1, y2 = S['blocks'][bi]
                 Hi, Wi = x_in.shape[2:]
                 Ho, Wo = y2.shape[2:]
-                b.c3.wgrad(y2, gm3, sums=True)
+                self._on_side(lambda x_=y2, g_=gm3: b.c3.wgrad(x_, g_, sums=True), y2, gm3)
                 gm2 = b.c3.dgrad(gm3, Ho, Wo, mask=y2)
-                b.c2.wgrad(y1, gm2, sums=True)
+                self._on_side(lambda x_=y1, g_=gm2: b.c2.wgrad(x_, g_, sums=True), y1, gm2)
                 gm1 = b.c2.dgrad(gm2, Hi, Wi, mask=y1)
-                b.c1.wgrad(x_in, gm1, sums=True)
+                self._on_side(lambda x_=x_in, g_=gm1: b.c1.wgrad(x_, g_, sums=True), x_in, gm1)
                 first = si == 0 and k == 0
                 # the block input is the previous block's ReLU output (mask) - and, at a stage boundary, also a decoder input
                 extra = g_feat[si - 1] if (k == 0 and si > 0) else None
                 if b.ds is not None:
-                    b.ds.wgrad(x_in, gm3, sums=True)
+                    self._on_side(lambda x_=x_in, g_=gm3: b.ds.wgrad(x_, g_, sums=True), x_in, gm3)
                     g_ds = b.ds.dgrad(gm3, Hi, Wi, round_out=False)
                     g_in = b.c1.dgrad(gm1, Hi, Wi, res=g_ds, res2=extra, mask=None if first else x_in, round_out=not first)
                 else:
                     g_in = b.c1.dgrad(gm1, Hi, Wi, res=gm3, res2=extra, mask=x_in)
                 gm3 = g_in
             if self.grad_hook is not None and si in (3, 2):
+                self._side_join()        # the gradients of this block are final only when its weight-gradient launches are done
                 self.grad_hook('decoder+layer4' if si == 3 else 'layer3')
         a0 = S['a0']
         g_a0 = co.maxpool_bwd(g_in, S['pool_idx'], a0.shape[2], a0.shape[3])
         nm, ns = (_NORM_MEAN, _NORM_STD) if self.normalize else (None, None)
         co.stem_wgrad(S['x'], g_a0, a0, self.stem_conv, self.stem_bn, nm, ns)
+        self._side_join()
         if self.grad_hook is not None:
             self.grad_hook('rest')
 

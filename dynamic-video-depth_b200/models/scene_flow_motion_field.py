@@ -326,8 +326,10 @@ class Model(NetInterface):
     _GRAPH_KEYS = ('img_1', 'img_2', 'mask_2', 'R_1_T', 'R_2_T', 't_1', 't_2', 'flow_1_2', 'K', 'K_inv', 'motion_seg_1', 'time_stamp_1')
 
     def _graph_ok(self):
-        return (getattr(self.opt, 'cuda_graph', True) and self._world == 1 and self.device.type == 'cuda' and self.opt.midas
-                and not getattr(self, '_graph_broken', False))
+        # with several ranks the captured step contains the bucketed NCCL all-reduces (side stream forked from and joined to the
+        # capture stream): every rank captures at the same step because the step signature (pairs, gap, phase) is rank-uniform
+        return (getattr(self.opt, 'cuda_graph', True) and (self._world == 1 or getattr(self.opt, 'cuda_graph_dist', True))
+                and self.device.type == 'cuda' and self.opt.midas and not getattr(self, '_graph_broken', False))
 
     def _graph_step(self, b, steps, dt):
         B = b['img_1'].shape[0]
@@ -353,7 +355,8 @@ class Model(NetInterface):
             g = torch.cuda.CUDAGraph()
             n0 = ops.LAUNCHES['n']
             try:
-                with torch.cuda.graph(g, pool=self._graph_pool):
+                # thread_local: NCCL's watchdog thread queries events while this thread captures
+                with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode='thread_local'):
                     dev_logs, d1, d2, sf, poses = self._step_body(static, steps, dt)
                     ent['pinned'].copy_(dev_logs, non_blocking=True)
             except Exception as e:   # noqa: BLE001  capture is an optimisation: report and keep stepping eagerly
@@ -384,6 +387,15 @@ class Model(NetInterface):
         self.graph_stats['replayed'] += 1
         torch.cuda.current_stream().synchronize()      # the log of THIS step (NaN guard of the loggers), no run-ahead needed
         return ent['pinned'].clone(), ent['vis']
+
+    def release_graphs(self):
+        """Drop every captured step graph (and its static buffers). Required before torch.distributed.destroy_process_group():
+        NCCL does not tear a communicator down while CUDA graphs that captured its collectives are alive."""
+        if getattr(self, '_graphs', None):
+            torch.cuda.synchronize()
+            self._graphs.clear()
+            self._graph_pool = None
+            torch.cuda.synchronize()
 
     def _dump_visual(self, epoch, batch_ind, indx, batch, d1, d2, sf, poses):
         """The 13 `pred` arrays of the reference (smf.py:201-202, video_base.py:105-126), materialised only

@@ -5,6 +5,7 @@ happens inside libdvd_b200.so. Argument / shape / dtype / contiguity violations 
 before any launch; a non-zero return from the library raises RuntimeError.
 """
 import ctypes
+import os
 
 import torch
 
@@ -290,6 +291,17 @@ def mlp_chain_fwd(packed, p0, t0, dt, n_eval, n_acc, save=False, want_steps=True
     return {'acc': acc, 's_steps': s_steps, 'p_steps': p_steps, 'save': sv}
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(idx)
+    if st is None:
+        st = _SIDE_STREAMS[idx] = torch.cuda.Stream(device=idx)
+    return st
+
+
 def mlp_chain_bwd(packed, fwd, t0, dt, n_acc, g_acc, g_steps, grad_w, grad_b):
     """Raw backward over all evals: dgrad chain + wgrad per eval (descending).
     g_acc [B,3,H,W] or None; g_steps: list (len n_eval) of [B,3,H,W] or None entries.
@@ -301,13 +313,24 @@ def mlp_chain_bwd(packed, fwd, t0, dt, n_acc, g_acc, g_steps, grad_w, grad_b):
     dev = p_steps.device
     lib = _lib.load()
     per = lib.dvd_mlp_save_bytes_per_eval(ctypes.byref(cfg), npx)
-    dy = torch.empty(lib.dvd_mlp_dy_bytes(ctypes.byref(cfg), npx), dtype=torch.uint8, device=dev)
+    # Two streams: the weight gradient of evaluation e (HBM-bound: it streams the saved activations) runs on a side stream while the
+    # main stream continues with the data gradient of evaluation e - 1 (tensor-bound). dY is double-buffered; the data gradient that
+    # re-uses a dY buffer waits for the weight gradient that read it two evaluations earlier.
+    overlap = os.environ.get('DVD_BWD_OVERLAP', '1') != '0' and n_eval > 1
+    nbuf = 2 if overlap else 1
+    dys = [torch.empty(lib.dvd_mlp_dy_bytes(ctypes.byref(cfg), npx), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    side = _side_stream(dev) if overlap else None
+    main = torch.cuda.current_stream()
+    wdone = [None] * nbuf
     a = None
     gb5 = grad_b[5]
     if gb5.numel() != 3:
         raise ValueError('grad of the output bias must have 3 elements')
     gw_arr, gb_arr = _ptr_array(grad_w), _ptr_array(grad_b)
-    for e in range(n_eval - 1, -1, -1):
+    for i, e in enumerate(range(n_eval - 1, -1, -1)):
+        dy = dys[i % nbuf]
+        if wdone[i % nbuf] is not None:
+            main.wait_event(wdone[i % nbuf])
         a_out = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
         gs = g_steps[e] if g_steps is not None else None
         save_e = ctypes.c_void_p(sv.data_ptr() + e * per)
@@ -316,11 +339,23 @@ def mlp_chain_bwd(packed, fwd, t0, dt, n_acc, g_acc, g_steps, grad_w, grad_b):
                                      _ptr(t0) if cfg.time_dependent else ctypes.c_void_p(0), float(dt), e,
                                      int(e < n_acc and g_acc is not None), _ptr(g_acc), _ptr(gs), _ptr(a), _ptr(a_out),
                                      save_e, _ptr(dy), _ptr(gb5), npx, hw, _stream()), 'dvd_mlp_dgrad')
-        LAUNCHES['n'] += 1
-        _lib.check(lib.dvd_mlp_wgrad(ctypes.byref(cfg), save_e, _ptr(dy), gw_arr, gb_arr, npx, _stream()),
-                   'dvd_mlp_wgrad')
         a = a_out
-    return a
+        LAUNCHES['n'] += 1
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                _lib.check(lib.dvd_mlp_wgrad(ctypes.byref(cfg), save_e, _ptr(dy), gw_arr, gb_arr, npx, _stream()), 'dvd_mlp_wgrad')
+                wdone[i % nbuf] = torch.cuda.Event()
+                wdone[i % nbuf].record(side)
+        else:
+            _lib.check(lib.dvd_mlp_wgrad(ctypes.byref(cfg), save_e, _ptr(dy), gw_arr, gb_arr, npx, _stream()), 'dvd_mlp_wgrad')
+    if side is not None:       # join: the weight gradients are final (and dY / the saved activations may be freed) after this
+        for ev in wdone:
+            if ev is not None:
+                main.wait_event(ev)
+    return a_out
 
 
 def acc_reg(s0, s1, acc_mul, gscale=1.0, want_grad=True):

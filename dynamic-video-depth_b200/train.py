@@ -86,6 +86,7 @@ def main_worker(local_rank, ngpus, opt):
         for e, log in logger.epoch_logs:
             print('epoch %d:' % e, {k: round(v, 6) for k, v in log.items()})
     if distributed:
+        model.release_graphs()
         dist.destroy_process_group()
 
 

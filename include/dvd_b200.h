@@ -105,6 +105,9 @@ int dvd_reproject_materialize_bwd(const float* depth_1, const float* depth_2, co
  * memory; passes 1 = bf16, 3 = bf16x3 split (fp32-grade). Not on the hot path.                 */
 int dvd_selftest_umma(const float* A, const float* B, float* D, int K, int N, int mode, int passes,
                       void* stream);
+/* hardware probe (no product path uses it yet): a tcgen05 K-major SWIZZLE_128B operand read through a descriptor that starts
+ * `shift` 128-byte rows into the image with 8-row groups `sbo_rows` rows apart (halo-resident convolution tiles).          */
+int dvd_selftest_halo(const float* A, const float* B, float* D, int R, int N, int shift, int sbo_rows, int bo_mode, void* stream);
 
 /* ---- scene-flow MLP (M1-M4, L2) ---------------------------------------------------------------
  * networks/blocks.py:19-34 (PeriodicEmbed), networks/sceneflow_field.py:20-53 (SceneFlowFieldNet:

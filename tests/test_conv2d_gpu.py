@@ -167,6 +167,35 @@ def test_stream_k_schedule_matches_whole_tiles_and_leaves_flags_clear():
     assert float(ws[256:].abs().max()) > 0, 'these shapes are expected to take the stream-K schedule'
 
 
+@pytest.mark.parametrize('nt', [160, 192, 224, 128])
+def test_ragged_channel_tiles_match_torch_fp64(nt):
+    """Cout = 1024 with channel tiles of `nt` (DVD_CONV_NT): the last tile is ragged in whole 32-channel blocks - its weight rows
+    beyond Cout are zero-filled by the TMA unit and its epilogue skips them (BatchNorm + residual + ReLU + mask all indexed there)."""
+    import os
+    from dvd_b200 import conv_ops as co
+    g = gen(300 + nt)
+    N, H, W, ci, co_ = 3, 14, 24, 512, 1024
+    conv = make_conv(ci, co_, 1, 1, 1, False, 301)
+    bn = make_bn(co_, 302)
+    x = tf32(torch.randn(N, ci, H, W, generator=g))
+    res = torch.randn(N, co_, H, W, generator=g)
+    mask = torch.randn(N, co_, H, W, generator=g)
+    ref = F.conv2d(x.double(), tf32(conv.weight.detach()).double())
+    ref = F.batch_norm(ref, bn.running_mean.double(), bn.running_var.double(), bn.weight.double(), bn.bias.double(), False, 0.0, bn.eps)
+    ref = (ref + res.double()).relu() * (mask > 0)
+    conv, bn = conv.cuda(), bn.cuda()
+    c = co.Conv(conv, bn)
+    c.pack(need_bwd=False)
+    d = co.make_desc(N, H, W, ci, H, W, co_, co.fwd_taps(1, 0), 1, 0, relu=True, round_out=False, bn_eps=bn.eps)
+    os.environ['DVD_CONV_NT'] = str(nt)
+    try:
+        y = co.conv2d_launch(d, cl(x), c.w_fwd, torch.full((N, co_, H, W), float('nan'), device='cuda').contiguous(memory_format=torch.channels_last),
+                             None, c._bn_fwd(), cl(res), None, cl(mask))
+    finally:
+        del os.environ['DVD_CONV_NT']
+    assert rel_err(y, ref) < TOL
+
+
 DGRAD_CASES = [
     # N, H,  W,  Cin,  Cout, k, stride, groups, bn, res, mask
     (2, 28, 48, 64, 128, 3, 1, 1, False, True, True),
