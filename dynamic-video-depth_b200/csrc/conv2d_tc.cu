@@ -65,6 +65,12 @@ struct ConvParams {
   int pair;                       // csize == 2 as ONE tcgen05 CTA pair (cta_group::2): M = 256 pixels per MMA, each CTA keeps its own
                                   // 128-pixel A tile and HALF of the weight tile in shared memory (the tensor core reads both halves),
                                   // so the per-SM shared-memory traffic of the weight operand - the measured bound - halves
+  int halo;                       // halo-resident activation tiles (stride-1 stencils): per 32-channel chunk ONE TMA box of the 16 x 8 pixel
+                                  // tile plus its stencil halo instead of one box per tap; a tap is a row offset of the MMA's A descriptor
+                                  // (8-pixel tile rows = the descriptor's 8-row groups, pitch HW rows apart). The A traffic of a k x k layer
+                                  // drops by k*k * 128 / (HW * HH); weights stream through their own ring, one box per (chunk, tap)
+  int HW, HH, dy0, dx0;           // halo box in pixels and the offset of its origin from the tile origin (= the smallest tap offsets)
+  int a_box, a_stage, nA, nW;     // bytes of a halo box / of its 1024-aligned stage, stages of the two rings
   int sk;                         // stream-K: the (tile, K-step) work list is cut into one contiguous range per cluster instead of
                                   // whole tiles round-robin; a tile cut by a range boundary is finished by the cluster that owns its
                                   // FIRST K-steps (it reaches that tile last), the others leave raw partial accumulators in `ws`
@@ -223,6 +229,16 @@ __device__ __forceinline__ void umma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, u
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// K-major SWIZZLE_128B descriptor whose 8-row groups are `sbo_bytes` apart (halo boxes: the pitch of a tile row); the start may
+// be any 128-byte row of the image: the swizzle is a function of the absolute shared-memory address (profiles/r3_probe_halo_*)
+__device__ __forceinline__ uint64_t make_sdesc_k_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ float round_tf32(float v) {
   uint32_t o;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(o) : "f"(v));
@@ -292,11 +308,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
                                                                const __grid_constant__ ConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* full = bars;                       // [kStages]
-  uint64_t* empty = bars + kStages;            // [kStages]
-  uint64_t* acc_full = bars + 2 * kStages;     // [2]
-  uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* full = bars;                       // [8]  stage ring (halo mode: the weight ring)
+  uint64_t* empty = bars + 8;                  // [8]
+  uint64_t* fullA = bars + 16;                 // [4]  halo mode: ring of halo boxes
+  uint64_t* emptyA = bars + 20;                // [4]
+  uint64_t* acc_full = bars + 24;              // [2]
+  uint64_t* acc_empty = bars + 26;             // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
   float* aff_mem = reinterpret_cast<float*>(smem + kOffAff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -304,13 +322,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
     printf("dvd_b200: conv2d_tc_kernel: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
+  // halo mode: byte offset of every tap into the halo box, and its weight image index
+  // (the last KB of the ring area: the host leaves it free in halo mode)
+  uint32_t* tap_off = reinterpret_cast<uint32_t*>(smem + (size_t)kStages * kStageBytes - 1024);
+  int* tap_wt = reinterpret_cast<int*>(tap_off + DVD_CONV_MAX_TAPS);
+  if (P.halo) {
+    for (int t = threadIdx.x; t < P.d.ntaps; t += blockDim.x) {
+      tap_off[t] = (uint32_t)((P.d.dy[t] - P.dy0) * P.HW + (P.d.dx[t] - P.dx0)) * 128u;
+      tap_wt[t] = P.d.wt[t];
+    }
+  }
   if (warp == 1) {
     if (kPair) tmem_alloc_2sm(tmem_holder, 512);
     else tmem_alloc(tmem_holder, 512);
   } else if (warp == 0 && lane == 0) {
     // pair mode: one commit of the leader's MMA thread (multicast) frees a stage in both CTAs; the leader's accumulator is
     // drained by the epilogue threads of BOTH CTAs
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kPair ? 1u : (uint32_t)P.csize); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kPair ? 1u : (uint32_t)P.csize); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPair ? 512u : 256u); }
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -336,7 +365,106 @@ __global__ void __launch_bounds__(kThreads, 1) conv2d_tc_kernel(const __grid_con
   const uint32_t stage_tx = (uint32_t)kABytes + (uint32_t)P.NT * 128u;
   const int wslice = P.NT / P.csize;              // weight rows this CTA fetches (and multicasts) per stage
 
-  if (warp == 0) {
+  // halo mode: [nA halo stages | nW weight stages] in the ring area
+  uint8_t* const smemW = smem + (size_t)P.nA * P.a_stage;
+  if (warp == 0 && P.halo) {
+    // ===== TMA producer, halo mode: one halo box per tile and chunk, one weight box per (tile, chunk, tap) =====
+    // The halo boxes run AHEAD of the weight stream (up to nA chunks): a box of ~200 rows has a long latency, and the weight ring
+    // (which the same thread feeds, blocking) is only a few taps deep. A weight box of chunk c is never issued before the halo box
+    // of chunk c (the MMA thread consumes in that order: a blocking wait here can then only be on slots that free by themselves).
+    if (lane == 0) {
+      uint32_t itA = 0, sa = 0, pha = 0, sw = 0, phw = 0;
+      const uint32_t w_tx = (uint32_t)P.NT * 128u;
+      int tileA = cluster_id, kcA = 0;
+      auto issue_A = [&](bool blocking) -> bool {
+        if (tileA >= ntiles) return false;
+        if (blocking) mbar_wait(&emptyA[sa], pha ^ 1u);
+        else if (!mbar_try_wait(&emptyA[sa], pha ^ 1u)) return false;
+        const Tile T = decode_tile(P, tileA, m_tiles, mgroups, crank);
+        const int kbase = P.d.kblock ? (T.n0 / P.d.kblock) * P.d.kblock : 0;
+        uint8_t* dstA = smem + (size_t)sa * P.a_stage;
+        if (kPair) {
+          const uint32_t lbar = mapa_u32(smem_u32(&fullA[sa]), 0);
+          if (crank == 0) mbar_arrive_expect_tx(&fullA[sa], 2u * (uint32_t)P.a_box);
+          tma_load_4d_2sm(dstA, &mapA, kbase + kcA * 32, T.w0 + P.dx0, T.h0 + P.dy0, T.img, lbar);
+        } else {
+          mbar_arrive_expect_tx(&fullA[sa], (uint32_t)P.a_box);
+          tma_load_4d(dstA, &mapA, kbase + kcA * 32, T.w0 + P.dx0, T.h0 + P.dy0, T.img, &fullA[sa]);
+        }
+        ++itA;
+        if (++sa == (uint32_t)P.nA) { sa = 0; pha ^= 1u; }
+        if (++kcA == P.kchunks) { kcA = 0; tileA += n_clusters; }
+        return true;
+      };
+      uint32_t chunk = 0;                                   // chunks (tile, kc) whose weight stream has started
+      for (int tile = cluster_id; tile < ntiles; tile += n_clusters) {
+        const Tile T = decode_tile(P, tile, m_tiles, mgroups, crank);
+        for (int kc = 0; kc < P.kchunks; ++kc, ++chunk) {
+          while (itA <= chunk) issue_A(true);               // this chunk's halo box first
+          for (int t = 0; t < P.d.ntaps; ++t) {
+            if ((t & 3) == 0)                                   // then, now and again, further boxes into free slots
+              while (itA < chunk + (uint32_t)P.nA && issue_A(false)) {}
+            const uint32_t s = sw, ph = phw;
+            if (++sw == (uint32_t)P.nW) { sw = 0; phw ^= 1u; }
+            uint8_t* st = smemW + (size_t)s * w_tx;
+            const int wt = tap_wt[t];
+            mbar_wait(&empty[s], ph ^ 1u);
+            if (kPair) {
+              const uint32_t lbar = mapa_u32(smem_u32(&full[s]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)wslice * 128u);
+              tma_load_3d_2sm(st, &mapW, kc * 32, T.n0 + crank * wslice, wt, lbar);
+            } else {
+              mbar_arrive_expect_tx(&full[s], w_tx);
+              if (P.csize > 1) tma_load_3d_mc(st + crank * wslice * 128, &mapW, kc * 32, T.n0 + crank * wslice, wt, &full[s], cmask);
+              else tma_load_3d(st, &mapW, kc * 32, T.n0, wt, &full[s]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && P.halo) {
+    // ===== MMA issuer, halo mode: tap = row offset of the A descriptor into the resident halo box =====
+    // (this single thread is the issue path of the whole CTA: ring positions are carried as wrap-around counters, not computed
+    // with run-time divisions, and the tap offsets come from a table in shared memory)
+    if (lane == 0 && !(kPair && crank != 0)) {
+      const uint32_t idesc = make_idesc_tf32(kPair ? 256 : 128, P.NT);
+      const uint32_t sbo = (uint32_t)P.HW * 128u;
+      const uint32_t w_stage = (uint32_t)P.NT * 128u, w_base = smem_u32(smemW);
+      uint32_t sa = 0, pha = 0, sw = 0, phw = 0, lt = 0;
+      for (int tile = cluster_id; tile < ntiles; tile += n_clusters, ++lt) {
+        const uint32_t buf = lt & 1u, aph = (lt >> 1) & 1u;
+        mbar_wait(&acc_empty[buf], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem + buf * (uint32_t)kMaxNT;
+        for (int kc = 0; kc < P.kchunks; ++kc) {
+          mbar_wait(&fullA[sa], pha);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(smem) + sa * (uint32_t)P.a_stage;
+          for (int t = 0; t < P.d.ntaps; ++t) {
+            mbar_wait(&full[sw], phw);
+            tc_fence_after();
+            const uint32_t sb = w_base + sw * w_stage;
+            const uint32_t sa_t = abase + tap_off[t];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = make_sdesc_k_sw128_sbo(sa_t + ks * 32, sbo), bd = make_sdesc_k_sw128(sb + ks * 32);
+              if (kPair) umma_ss_tf32_2sm(d, ad, bd, idesc, (kc | t | ks) ? 1u : 0u);
+              else umma_ss_tf32(d, ad, bd, idesc, (kc | t | ks) ? 1u : 0u);
+            }
+            if (kPair) umma_commit_2sm_mc(&empty[sw], 3);
+            else if (P.csize > 1) umma_commit_mc(&empty[sw], cmask);
+            else umma_commit(&empty[sw]);
+            if (++sw == (uint32_t)P.nW) { sw = 0; phw ^= 1u; }
+          }
+          if (kPair) umma_commit_2sm_mc(&emptyA[sa], 3);      // the MMAs that read this halo box (in both CTAs) are done
+          else umma_commit(&emptyA[sa]);
+          if (++sa == (uint32_t)P.nA) { sa = 0; pha ^= 1u; }
+        }
+        if (kPair) umma_commit_2sm_mc(&acc_full[buf], 3);
+        else umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t it = 0;
@@ -1110,6 +1238,38 @@ extern "C" int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, con
   } else {
     pick_tile(d.OH, d.OW, 128, 128, &P.TW, &P.TH);   // the TMA box spans TW * stride <= 256 input pixels
   }
+  // Halo-resident tiles for the classes that are bound by the activation stream, not by the tensor cores: grouped layers (64-
+  // channel blocks) and layers with few output channels. Tile = 16 rows x 8 pixels (a tile row = one 8-row group of the MMA's A
+  // operand); per 32-channel chunk one box of (8 + dx range) x (16 + dy range) pixels replaces ntaps boxes of 128 pixels.
+  P.halo = 0;
+  if (!pointwise && d.stride == 1 && d.ntaps >= 2) {
+    int dy0 = 127, dy1 = -128, dx0 = 127, dx1 = -128;
+    for (int t = 0; t < d.ntaps; ++t) {
+      dy0 = d.dy[t] < dy0 ? d.dy[t] : dy0; dy1 = d.dy[t] > dy1 ? d.dy[t] : dy1;
+      dx0 = d.dx[t] < dx0 ? d.dx[t] : dx0; dx1 = d.dx[t] > dx1 ? d.dx[t] : dx1;
+    }
+    const int HW = 8 + dx1 - dx0, HH = 16 + dy1 - dy0;
+    const long a_box = (long)HW * HH * 128, a_stage = (a_box + 1023) / 1024 * 1024;
+    const bool legal = HW <= 256 && HH <= 256 && 2 * a_stage + 2 * (long)kMaxNT * 128 + 1024 <= (long)kStages * kStageBytes;
+    const int nt0 = d.kblock ? d.kblock : (d.Cout >= kMaxNT ? kMaxNT : d.Cout);
+    const long tiles_tap = (long)((d.OW + P.TW - 1) / P.TW) * ((d.OH + P.TH - 1) / P.TH);
+    const long tiles_halo = (long)((d.OW + 7) / 8) * ((d.OH + 15) / 16);
+    // bytes through the TMA unit per image and 32-channel chunk (weights: half a tile per CTA when two CTAs share them)
+    const long wb = (long)nt0 * 128 / 2;
+    const bool pays = tiles_halo * (a_box + d.ntaps * wb) * 10 < tiles_tap * d.ntaps * (16384 + wb) * 8;
+    // Measured (profiles/r3_halo_vs_taps.txt): correct for every stencil, 3-6x fewer activation bytes through L2 - and still 10-25 %
+    // SLOWER than one box per tap on the three classes it was built for (head 128->32, grouped 3x3, dense 3x3). With operands this
+    // small the step time is set by the single MMA-issuing thread and the latency of the small weight boxes, not by bytes; the
+    // traffic model below is therefore not used to switch the mode on. DVD_CONV_HALO=1 selects it wherever it is legal.
+    bool want = false;
+    (void)pays;
+    (void)nt0;
+    if (const char* ev = getenv("DVD_CONV_HALO")) want = legal && atoi(ev) != 0;
+    if (want) {
+      P.halo = 1; P.HW = HW; P.HH = HH; P.dy0 = dy0; P.dx0 = dx0; P.a_box = (int)a_box; P.a_stage = (int)a_stage;
+      P.TW = 8; P.TH = 16;
+    }
+  }
   P.tiles_w = (d.OW + P.TW - 1) / P.TW;
   P.tiles_h = (d.OH + P.TH - 1) / P.TH;
   P.tma_store = identity_out && (P.NT % 32 == 0);
@@ -1162,8 +1322,18 @@ extern "C" int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, con
     set_error("dvd_conv2d_nhwc: Cout=%d is not a multiple of the %d-channel tile", d.Cout, P.NT);
     return -2;
   }
+  if (P.halo) {
+    const long ring = (long)kStages * kStageBytes - 1024, wbytes = (long)P.NT * 128;      // 1 KB: the tap tables
+    P.nA = 4;
+    while (P.nA > 2 && (ring - (long)P.nA * P.a_stage) / wbytes < 4) --P.nA;
+    long nW = (ring - (long)P.nA * P.a_stage) / wbytes;
+    P.nW = (int)(nW > 8 ? 8 : nW);
+    DVD_ARG_CHECK(P.nW >= 2, "halo mode: the rings do not fit (box %d bytes, NT %d)", P.a_box, P.NT);
+  }
   CUtensorMap mapA, mapW, mapY;
-  if (int e = make_nhwc_map(&mapA, x, inN, inH, inW, d.Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  if (P.halo) {
+    if (int e = make_nhwc_map(&mapA, x, inN, inH, inW, d.Cin, P.HW, P.HH, 1, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  } else if (int e = make_nhwc_map(&mapA, x, inN, inH, inW, d.Cin, P.TW, P.TH, d.stride, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   {
     int max_wt = 0;
     for (int t = 0; t < d.ntaps; ++t) max_wt = d.wt[t] > max_wt ? d.wt[t] : max_wt;
@@ -1192,7 +1362,7 @@ extern "C" int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, con
     const double eff = (double)ctiles / (double)(waves * full);
     const char* ev = getenv("DVD_CONV_STREAMK");
     const bool allowed = !(ev && atoi(ev) == 0);
-    if (allowed && workspace && P.tma_store && ksteps >= 8 && eff < 0.88) {
+    if (allowed && workspace && P.tma_store && !P.halo && ksteps >= 8 && eff < 0.88) {
       const long min_units = ksteps / 4 > 8 ? ksteps / 4 : 8;
       long nc = total / min_units;
       if (nc > full) nc = full;

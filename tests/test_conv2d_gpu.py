@@ -196,6 +196,31 @@ def test_ragged_channel_tiles_match_torch_fp64(nt):
     assert rel_err(y, ref) < TOL
 
 
+@pytest.mark.parametrize('case', [(2, 30, 50, 128, 32, 3, 1), (1, 28, 48, 512, 512, 3, 32), (2, 20, 36, 64, 64, 5, 1), (1, 24, 40, 32, 32, 11, 1),
+                                  (2, 56, 96, 256, 256, 3, 1)])
+def test_halo_resident_tiles_match_torch_fp64(case):
+    """DVD_CONV_HALO=1: one TMA box per 32-channel chunk (tile + stencil halo), taps as row offsets of the MMA's A descriptor
+    (start addresses off the 8-row swizzle atom, 8-row groups one halo pitch apart). Opt-in mode: slower than one box per tap on
+    this network (profiles/r3_halo_vs_taps.txt), kept for the large-stencil classes."""
+    import os
+    from dvd_b200 import conv_ops as co
+    N, H, W, ci, co_, k, groups = case
+    g = gen(500 + k + ci)
+    conv = make_conv(ci, co_, k, 1, groups, True, 501 + k)
+    x = tf32(torch.randn(N, ci, H, W, generator=g))
+    res = torch.randn(N, co_, H, W, generator=g)
+    ref = (F.conv2d(x.double(), tf32(conv.weight.detach()).double(), conv.bias.double(), padding=k // 2, groups=groups) + res.double()).relu()
+    conv = conv.cuda()
+    c = co.Conv(conv, None)
+    c.pack(need_bwd=False)
+    os.environ['DVD_CONV_HALO'] = '1'
+    try:
+        y = c.fwd(cl(x), res=cl(res), relu=True, round_out=False)
+    finally:
+        del os.environ['DVD_CONV_HALO']
+    assert rel_err(y, ref) < TOL
+
+
 DGRAD_CASES = [
     # N, H,  W,  Cin,  Cout, k, stride, groups, bn, res, mask
     (2, 28, 48, 64, 128, 3, 1, 1, False, True, True),
