@@ -1305,13 +1305,28 @@ extern "C" int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, con
   // rounds wins when  rounds(NT) * t(NT)  is smaller, t(NT) = 0.47 + 0.53 * NT / 256 the measured relative cost of a K-step
   // (profiles/r2_conv_table: 3x3 256->256 at NT 256 vs 256->128 at NT 128). Dense layers with a TMA-store epilogue only; the
   // last tile may be ragged in whole 32-channel blocks.
-  if (!d.kblock && P.tma_store && d.Cout > kMaxNT && d.Cout % 32 == 0) {
+  if (!d.kblock && P.tma_store && d.Cout >= 128 && d.Cout % 32 == 0) {
     const char* ev = getenv("DVD_CONV_NT");
     if (ev && atoi(ev) >= 32 && atoi(ev) <= kMaxNT && atoi(ev) % 32 == 0) {
       P.NT = atoi(ev);
     } else if (!(ev && atoi(ev) == 0)) {
+      // a layer that cannot even fill one round with 256-wide tiles (small batches, low resolutions) may go down to 64
+      const int nt_max = d.Cout >= kMaxNT ? kMaxNT : d.Cout;
+      int nt_min = mgroups_h * ((d.Cout + nt_max - 1) / nt_max) < full ? 64 : 128;
+      {
+        // layers that will take the stream-K schedule (few tiles, long K loop) keep the widest tile: their K-steps are spread
+        // over all SMs whatever the tile count, and a wide step is the cheapest per output channel
+        const long ksteps = (long)d.ntaps * ((d.kblock ? d.kblock : d.Cin) / 32), tiles0 = mgroups_h * ((d.Cout + nt_max - 1) / nt_max);
+        const long waves0 = (tiles0 + full - 1) / full, total0 = tiles0 * ksteps, mu = ksteps / 4 > 8 ? ksteps / 4 : 8;
+        long nc0 = total0 / mu;
+        if (nc0 > full) nc0 = full;
+        const char* evs = getenv("DVD_CONV_STREAMK");
+        if (workspace && !P.halo && ksteps >= 8 && !(evs && atoi(evs) == 0) && nc0 >= 1 &&
+            waves0 * ksteps - (total0 + nc0 - 1) / nc0 >= 64)
+          nt_min = nt_max;
+      }
       double best = 1e30;
-      for (int nt = kMaxNT; nt >= 128; nt -= 32) {
+      for (int nt = nt_max; nt >= nt_min; nt -= 32) {
         const long tiles = mgroups_h * ((d.Cout + nt - 1) / nt);
         const double cost = (double)((tiles + full - 1) / full) * (0.47 + 0.53 * nt / 256.0);
         if (cost < best * 0.97) { best = cost; P.NT = nt; }      // a narrower tile must win by 3 %
