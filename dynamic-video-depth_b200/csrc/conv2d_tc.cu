@@ -807,21 +807,28 @@ __global__ void __launch_bounds__(256) conv_pack_batch_kernel(const dvd_pack_ite
     const int rows = mode ? Cin : Cout;
     const int cols = kblock ? kblock : (mode ? Cout : Cin);
     const long n = (long)k * k * rows * cols;
-    for (int e = threadIdx.x; e < kPackChunk; e += 256) {
+    // four consecutive elements per thread (cols is a multiple of 4: one index decomposition, one 16-byte store)
+    for (int e = threadIdx.x * 4; e < kPackChunk; e += 1024) {
       const long i = base + e;
       if (i >= n) break;
       const int c = (int)(i % cols);
       const long q = i / cols;
       const int r = (int)(q % rows), t = (int)(q / rows);
       const int ky = t / k, kx = t - ky * k;
-      const int cabs = kblock ? (r / kblock) * kblock + c : c;
-      const int co = mode ? cabs : r, ci = mode ? r : cabs;
-      float v = 0.f;
-      if (co / opg == ci / cpg) {
-        v = it.weight[co * it.s_co + (ci % cpg) * it.s_ci + ky * it.s_ky + kx * it.s_kx];
-        if (mode && it.bn_gamma) v *= it.bn_gamma[co] * rsqrtf(it.bn_var[co] + it.bn_eps);
+      const long tap = (long)ky * it.s_ky + (long)kx * it.s_kx;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cabs = kblock ? (r / kblock) * kblock + c + j : c + j;
+        const int co = mode ? cabs : r, ci = mode ? r : cabs;
+        v[j] = 0.f;
+        if (co / opg == ci / cpg) {
+          v[j] = it.weight[co * it.s_co + (ci % cpg) * it.s_ci + tap];
+          if (mode && it.bn_gamma) v[j] *= it.bn_gamma[co] * rsqrtf(it.bn_var[co] + it.bn_eps);
+        }
+        v[j] = round_tf32(v[j]);
       }
-      out[i] = round_tf32(v);
+      *reinterpret_cast<float4*>(out + i) = make_float4(v[0], v[1], v[2], v[3]);
     }
   }
 }
