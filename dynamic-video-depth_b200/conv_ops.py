@@ -185,11 +185,9 @@ class PackTable:
             it.s_co, it.s_ci, it.s_ky, it.s_kx = st
             it.Cout, it.Cin, it.ksize, it.groups, it.kblock = co, ci, kh, c.groups, c.kblock
             it.blk0 = blk
-            if ci % 4 or co % 4 or (c.kblock and c.kblock % 4):
-                raise ValueError('dvd_conv2d_pack_batch packs four consecutive channels per thread: channel counts must be multiples of 4')
             nb = lib.dvd_conv2d_pack_blocks(co, ci, kh, c.groups, c.kblock)
             if nb < 1:
-                raise ValueError('bad convolution shape in the pack table')
+                raise ValueError('dvd_conv2d_pack_batch works on 32 x 32 channel tiles: Cout, Cin (and kblock) must be multiples of 32')
             blk += nb
         raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8)
         self.table = raw.to(self.convs[0].conv.weight.device)

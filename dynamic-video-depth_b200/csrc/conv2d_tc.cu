@@ -788,10 +788,12 @@ __global__ void __launch_bounds__(256) conv_pack_kernel(const float* __restrict_
 
 // All layers of a net in ONE launch (the weights change every optimisation step, so every step re-packs ~250 images: as single
 // launches that is 123 grids of a few microseconds each). items[] lives in device memory; item i owns the blocks
-// [blk0[i], blk0[i+1]) of the grid, each block packs kPackChunk consecutive elements of both images.
-constexpr int kPackChunk = 2048;
+// [blk0[i], blk0[i+1]) of the grid.
+// One block = one 32 x 32 tile (out-channels x in-channels) of one tap: the forward image is written row by row, the data-gradient
+// image is the transposed tile (through shared memory), so that reads of the weights and writes of BOTH images are coalesced.
 __global__ void __launch_bounds__(256) conv_pack_batch_kernel(const dvd_pack_item* __restrict__ items, int n_items, int want_bwd) {
   DVD_PDL_ENTER();
+  __shared__ float tile[32][33];
   int lo = 0, hi = n_items - 1;
   while (lo < hi) {                       // last item whose first block is <= blockIdx.x
     const int mid = (lo + hi + 1) >> 1;
@@ -800,36 +802,31 @@ __global__ void __launch_bounds__(256) conv_pack_batch_kernel(const dvd_pack_ite
   const dvd_pack_item it = items[lo];
   const int Cout = it.Cout, Cin = it.Cin, k = it.ksize, kblock = it.kblock;
   const int cpg = Cin / it.groups, opg = Cout / it.groups;
-  const long base = ((long)blockIdx.x - it.blk0) * kPackChunk;
-  for (int mode = 0; mode < 2; ++mode) {
-    float* out = mode ? (want_bwd ? it.w_bwd : nullptr) : it.w_fwd;
-    if (!out) continue;
-    const int rows = mode ? Cin : Cout;
-    const int cols = kblock ? kblock : (mode ? Cout : Cin);
-    const long n = (long)k * k * rows * cols;
-    // four consecutive elements per thread (cols is a multiple of 4: one index decomposition, one 16-byte store)
-    for (int e = threadIdx.x * 4; e < kPackChunk; e += 1024) {
-      const long i = base + e;
-      if (i >= n) break;
-      const int c = (int)(i % cols);
-      const long q = i / cols;
-      const int r = (int)(q % rows), t = (int)(q / rows);
-      const int ky = t / k, kx = t - ky * k;
-      const long tap = (long)ky * it.s_ky + (long)kx * it.s_kx;
-      float v[4];
+  const int cols = kblock ? kblock : Cin;                 // columns of a forward-image row
+  const int nct = cols / 32, nrt = Cout / 32;
+  const int tt = (int)((long)blockIdx.x - it.blk0);
+  const int t = tt / (nrt * nct), rem = tt - t * (nrt * nct);
+  const int co0 = (rem / nct) * 32, c0 = (rem % nct) * 32;
+  const int base = kblock ? (co0 / kblock) * kblock : 0;  // first channel of the block-diagonal block (grouped)
+  const int ky = t / k, kx = t - ky * k;
+  const long tap = (long)ky * it.s_ky + (long)kx * it.s_kx;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  float* bwd = want_bwd ? it.w_bwd : nullptr;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cabs = kblock ? (r / kblock) * kblock + c + j : c + j;
-        const int co = mode ? cabs : r, ci = mode ? r : cabs;
-        v[j] = 0.f;
-        if (co / opg == ci / cpg) {
-          v[j] = it.weight[co * it.s_co + (ci % cpg) * it.s_ci + tap];
-          if (mode && it.bn_gamma) v[j] *= it.bn_gamma[co] * rsqrtf(it.bn_var[co] + it.bn_eps);
-        }
-        v[j] = round_tf32(v[j]);
-      }
-      *reinterpret_cast<float4*>(out + i) = make_float4(v[0], v[1], v[2], v[3]);
-    }
+  for (int i = 0; i < 4; ++i) {
+    const int row = wy * 4 + i, co = co0 + row, ci = base + c0 + lane;
+    float v = 0.f;
+    if (co / opg == ci / cpg) v = it.weight[co * it.s_co + (ci % cpg) * it.s_ci + tap];
+    if (it.w_fwd) it.w_fwd[((long)t * Cout + co) * cols + c0 + lane] = round_tf32(v);
+    if (bwd) tile[row][lane] = it.bn_gamma ? v * it.bn_gamma[co] * rsqrtf(it.bn_var[co] + it.bn_eps) : v;
+  }
+  if (!bwd) return;
+  __syncthreads();
+  const int cols_b = kblock ? kblock : Cout;              // columns of a data-gradient-image row
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = wy * 4 + i, ci = base + c0 + row;     // row of the transposed tile = in-channel
+    bwd[((long)t * Cin + ci) * cols_b + (co0 - base) + lane] = round_tf32(tile[lane][row]);
   }
 }
 
@@ -1432,9 +1429,8 @@ extern "C" int dvd_conv2d_pack(const float* weight, long stride_co, long stride_
 }
 
 extern "C" long dvd_conv2d_pack_blocks(int Cout, int Cin, int ksize, int groups, int kblock) {
-  if (Cout < 1 || Cin < 1 || ksize < 1 || groups < 1) return -1;
-  const long n = (long)ksize * ksize * (Cout > Cin ? Cout : Cin) * (kblock ? kblock : (Cout > Cin ? Cin : Cout));
-  return (n + kPackChunk - 1) / kPackChunk;
+  if (Cout < 32 || Cin < 32 || ksize < 1 || groups < 1 || Cout % 32 || Cin % 32 || (kblock && kblock % 32)) return -1;
+  return (long)ksize * ksize * (Cout / 32) * ((kblock ? kblock : Cin) / 32);      // one block per 32 x 32 tile and tap
 }
 
 extern "C" int dvd_conv2d_pack_batch(const dvd_pack_item* items_dev, int n_items, long total_blocks, int want_bwd, void* stream) {

@@ -43,6 +43,7 @@ class FlatParams:
             view.copy_(p.data)
             p.data = view
             p.grad = self._view(self.grad, p, o)
+            p._dvd_flat_grad = True     # kernels may accumulate straight into .grad (ops.BnAct, depth_engine): explicit opt-in
 
     def _view(self, buf, p, o):
         flat = buf[o:o + p.numel()]

@@ -453,10 +453,14 @@ class BnAct(torch.autograd.Function):
         gx = torch.empty_like(x)
         gres = torch.empty_like(x) if ctx.has_res else None
         beta = ctx.beta
-        # The per-channel sums are atomically ACCUMULATED by the kernel. When gamma/beta already own a .grad buffer
-        # (the flat gradient buffer of dvd_b200.flat.FlatParams, zeroed once per step) they are accumulated there
-        # directly and autograd gets None (= zero) for them: no fill, no extra add kernels.
-        direct = (gamma.requires_grad and beta.requires_grad and gamma.grad is not None and beta.grad is not None
+        # The per-channel sums are atomically ACCUMULATED by the kernel. When gamma/beta live in the flat gradient buffer of
+        # dvd_b200.flat.FlatParams (zeroed once per step) they are accumulated there directly and autograd gets None (= zero)
+        # for them: no fill, no extra add kernels.
+        # Explicit opt-in: only parameters that dvd_b200.flat.FlatParams has re-homed carry `_dvd_flat_grad` (set there, cleared
+        # nowhere else); any other parameter gets its gradient through autograd like every other tensor, so torch.autograd.grad,
+        # hooks and foreign optimisers keep working.
+        direct = (getattr(gamma, '_dvd_flat_grad', False) and getattr(beta, '_dvd_flat_grad', False)
+                  and gamma.requires_grad and beta.requires_grad and gamma.grad is not None and beta.grad is not None
                   and gamma.grad.is_contiguous() and beta.grad.is_contiguous() and gamma.grad.dtype == torch.float32)
         if direct:
             gg, gb = gamma.grad, beta.grad

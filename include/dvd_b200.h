@@ -247,8 +247,8 @@ int dvd_conv2d_pack(const float* weight, long stride_co, long stride_ci, long st
 
 /* The same for every layer of a net in ONE launch. `items_dev` is a table of n_items entries in DEVICE memory (the pointers in
  * it are device pointers; the caller rebuilds it when a tensor moves). Entry i owns grid blocks [blk0, blk0 + blocks_i) with
- * blocks_i = dvd_conv2d_pack_blocks(...) and blk0 the running sum; total_blocks = the sum over all entries. Channel counts
- * (and kblock) must be multiples of 4; the images must be 16-byte aligned.                                                     */
+ * blocks_i = dvd_conv2d_pack_blocks(...) (one block per 32 x 32 channel tile and tap; -1 unless Cout, Cin and kblock are
+ * multiples of 32) and blk0 the running sum; total_blocks = the sum over all entries.                                           */
 typedef struct dvd_pack_item {
   const float* weight;      /* [Cout, Cin/groups, k, k], element strides below */
   float* w_fwd;             /* forward image or NULL */

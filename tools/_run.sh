@@ -1,3 +1,4 @@
 set -x
-timeout 300 python -m pytest tests/test_conv2d_gpu.py tests/test_depth_engine_gpu.py -x -q 2>&1 | tail -3
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r3_bench_2gpu_full.log 2>gpurun_out/r3_bench_2gpu_full.err; echo "rc=$?"; tail -c 600 gpurun_out/r3_bench_2gpu_full.log; tail -5 gpurun_out/r3_bench_2gpu_full.err
+timeout 300 python -m pytest tests/test_conv2d_gpu.py tests/test_depth_engine_gpu.py tests/test_step_gpu.py -x -q 2>&1 | tail -3
+timeout 200 python bench.py --steps 20 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_pack3.log 2>&1; tail -c 300 gpurun_out/r3_bench_pack3.log
+timeout 200 python bench.py --pairs 1 --steps 30 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_pack3_B1.log 2>&1; tail -c 300 gpurun_out/r3_bench_pack3_B1.log
