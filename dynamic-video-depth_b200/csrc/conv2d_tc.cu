@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(256) conv_pack_batch_kernel(const dvd_pack_ite
     float v = 0.f;
     if (co / opg == ci / cpg) v = it.weight[co * it.s_co + (ci % cpg) * it.s_ci + tap];
     if (it.w_fwd) it.w_fwd[((long)t * Cout + co) * cols + c0 + lane] = round_tf32(v);
-    if (bwd) tile[row][lane] = it.bn_gamma ? v * it.bn_gamma[co] * rsqrtf(it.bn_var[co] + it.bn_eps) : v;
+    if (bwd) tile[row][lane] = it.bn_gamma ? v * (it.bn_gamma[co] * rsqrtf(it.bn_var[co] + it.bn_eps)) : v;   // same association as conv_pack_kernel
   }
   if (!bwd) return;
   __syncthreads();

@@ -221,6 +221,41 @@ def test_halo_resident_tiles_match_torch_fp64(case):
     assert rel_err(y, ref) < TOL
 
 
+def test_batched_pack_is_bit_identical_to_single_layer_pack():
+    """dvd_conv2d_pack_batch (one launch for a whole net: 32 x 32 transposed tiles, device-resident table) writes exactly the images
+    dvd_conv2d_pack writes layer by layer: dense 1x1 / 3x3 with and without BatchNorm, Cin != Cout, grouped with 8 / 32 / 64
+    channels per group."""
+    from dvd_b200 import conv_ops as co
+    specs = [(256, 512, 1, 1, True), (512, 256, 3, 1, False), (128, 32, 3, 1, False), (256, 256, 3, 32, True), (1024, 1024, 3, 32, True),
+             (2048, 2048, 3, 32, True), (64, 256, 1, 1, True)]
+    convs = []
+    for i, (ci, co_, k, g, use_bn) in enumerate(specs):
+        conv = make_conv(ci, co_, k, 1, g, not use_bn, 900 + i).cuda()
+        bn = make_bn(co_, 950 + i).cuda() if use_bn else None
+        # the flat parameter buffers of the engine hold convolution weights channels-last: same strides here
+        conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+        convs.append(co.Conv(conv, bn))
+    ref = []
+    for c in convs:
+        c.pack()
+        ref.append((c.w_fwd.clone(), c.w_bwd.clone()))
+        c.w_fwd.fill_(float('nan'))
+        c.w_bwd.fill_(float('nan'))
+    table = co.PackTable(convs)
+    table.pack(need_bwd=True)
+    torch.cuda.synchronize()
+    for c, (f, b) in zip(convs, ref):
+        assert torch.equal(c.w_fwd, f) and torch.equal(c.w_bwd, b)
+    # forward images only (evaluation): the data-gradient images are left alone
+    for c in convs:
+        c.w_fwd.fill_(0.0)
+        c.w_bwd.fill_(7.0)
+    table.pack(need_bwd=False)
+    torch.cuda.synchronize()
+    for c, (f, b) in zip(convs, ref):
+        assert torch.equal(c.w_fwd, f) and bool((c.w_bwd == 7.0).all())
+
+
 DGRAD_CASES = [
     # N, H,  W,  Cin,  Cout, k, stride, groups, bn, res, mask
     (2, 28, 48, 64, 128, 3, 1, 1, False, True, True),

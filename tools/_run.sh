@@ -1,4 +1,3 @@
 set -x
-timeout 300 python -m pytest tests/test_conv2d_gpu.py tests/test_depth_engine_gpu.py tests/test_step_gpu.py -x -q 2>&1 | tail -3
-timeout 200 python bench.py --steps 20 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_pack3.log 2>&1; tail -c 300 gpurun_out/r3_bench_pack3.log
-timeout 200 python bench.py --pairs 1 --steps 30 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_pack3_B1.log 2>&1; tail -c 300 gpurun_out/r3_bench_pack3_B1.log
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/r3_tests6.log 2>&1; tail -4 gpurun_out/r3_tests6.log
+timeout 500 python bench.py > gpurun_out/r3_bench_final.log 2>gpurun_out/r3_bench_final.err; tail -c 300 gpurun_out/r3_bench_final.log
