@@ -93,20 +93,30 @@ def make_desc(N, H, W, Cin, OH, OW, Cout, taps, stride=1, kblock=0, YH=None, YW=
 # ------------------------------------------------------------------------------------------------
 # raw launches
 
-_WORKSPACE = {}     # device index -> zero-initialised exchange area of the stream-K schedule (dvd_conv2d_nhwc_ws)
+_WORKSPACE = {}     # (device index, lane) -> zero-initialised exchange area of the stream-K schedule (dvd_conv2d_nhwc_ws)
+_WS_LANE = 0
+
+
+def set_workspace_lane(lane):
+    """Convolutions that may run CONCURRENTLY (the lanes of depth_engine.MidasEngine: one stream each) must not share an exchange
+    area; launches of one lane are stream-ordered. Returns the previous lane."""
+    global _WS_LANE
+    prev, _WS_LANE = _WS_LANE, int(lane)
+    return prev
 
 
 def conv_workspace(device):
-    """The per-device exchange area of the convolution kernel's stream-K schedule. One area per device: all convolutions of a
-    process are issued on one stream at a time (the current stream, or the capture stream of the step graph); a caller that
-    runs convolutions concurrently on several streams must set DVD_CONV_STREAMK=0. Never allocated during a graph capture."""
-    idx = device.index if device.index is not None else torch.cuda.current_device()
+    """The exchange area of the convolution kernel's stream-K schedule for the current lane of this device. All convolutions of a
+    lane are issued on one stream at a time (the current stream, or the capture stream of the step graph); a caller that runs
+    convolutions concurrently on several streams outside the engine's lanes must set DVD_CONV_STREAMK=0. Never allocated during a
+    graph capture (the eager warm-up steps before a capture have the same lanes)."""
+    idx = (device.index if device.index is not None else torch.cuda.current_device(), _WS_LANE)
     ws = _WORKSPACE.get(idx)
     if ws is None:
         if torch.cuda.is_current_stream_capturing():
             return None
-        ws = torch.zeros(_lib.load().dvd_conv2d_workspace_bytes() // 4, dtype=torch.float32, device=torch.device('cuda', idx))
-        torch.cuda.current_stream(idx).synchronize()
+        ws = torch.zeros(_lib.load().dvd_conv2d_workspace_bytes() // 4, dtype=torch.float32, device=torch.device('cuda', idx[0]))
+        torch.cuda.current_stream(idx[0]).synchronize()
         _WORKSPACE[idx] = ws
     return ws
 

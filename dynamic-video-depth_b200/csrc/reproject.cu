@@ -750,6 +750,9 @@ struct GlobalTaps {
 __device__ __forceinline__ void red_global_v2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
+__device__ __forceinline__ void red_global_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // scatter-add of the four tap gradients of one pixel; the packed kernels require W % 4 == 0, so whenever the nw tap sits
 // on an even column the (nw, ne) and (sw, se) taps are two 8-byte aligned pairs: one vector reduction each
 __device__ __forceinline__ void scatter4_global(float* q, int i00, int sx1, int sy1, const float (&g)[4]) {
@@ -759,6 +762,11 @@ __device__ __forceinline__ void scatter4_global(float* q, int i00, int sx1, int 
       if (sy1 != 0) red_global_v2(q + sy1, g[2], g[3]);
       else red_global_v2(q, g[2], g[3]);     // clamped bottom row: both weights are exactly 0 here, kept for form
     }
+  } else if (((i00 & 3) == 1) && sx1 == 1) {
+    // odd column whose pair still lies inside one 16-byte quad: one 4-wide reduction {0, g, g, 0} per row instead of two
+    // scalar ones (the LSU's reduction rate is per active lane, not per byte: DESIGN.md 8)
+    if (g[0] != 0.f || g[1] != 0.f) red_global_v4(q - 1, 0.f, g[0], g[1], 0.f);
+    if (g[2] != 0.f || g[3] != 0.f) red_global_v4(q - 1 + sy1, 0.f, g[2], g[3], 0.f);
   } else {
     if (g[0] != 0.f) atomicAdd(q, g[0]);
     if (g[1] != 0.f) atomicAdd(q + sx1, g[1]);

@@ -70,3 +70,32 @@ def test_midas_engine_uses_no_library_kernels():
     lib = [n for n in names if any(s in n.lower() for s in ('cudnn', 'cutlass', 'xmma', 'implicit_gemm', 'batch_norm', 'convolve'))]
     assert not lib, lib
     assert any('conv2d_tc_kernel' in n for n in names) and any('conv_wgrad_kernel' in n for n in names)
+
+
+def test_stream_schedules_agree(monkeypatch):
+    """The engine's stream schedules are pure re-orderings: single stream (DVD_BWD_OVERLAP=0), two-stream backward (default) and
+    two image lanes (DVD_LANES=2, opt-in) give the same depth map bit for bit and the same parameter gradients up to the order
+    of the fp32 atomics in the weight-gradient reductions."""
+    net = _nets().cuda()
+    x = torch.rand(4, 3, 64, 96, device='cuda')
+    w = torch.rand(4, 1, 64, 96, device='cuda')
+
+    def run(env):
+        for k in ('DVD_BWD_OVERLAP', 'DVD_LANES'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for p in net.parameters():
+            p.grad = None
+        d = net(x)
+        (d * w).sum().backward()
+        torch.cuda.synchronize()
+        return d.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+
+    d0, g0 = run({'DVD_BWD_OVERLAP': '0'})
+    for env in ({}, {'DVD_LANES': '2'}):
+        d1, g1 = run(env)
+        assert torch.equal(d0, d1), env
+        num = sum(float(((g1[k].double() - g0[k].double()) ** 2).sum()) for k in g0)
+        den = sum(float((g0[k].double() ** 2).sum()) for k in g0)
+        assert (num / den) ** 0.5 < 1e-5, (env, (num / den) ** 0.5)
