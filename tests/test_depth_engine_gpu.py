@@ -74,8 +74,8 @@ def test_midas_engine_uses_no_library_kernels():
 
 def test_stream_schedules_agree(monkeypatch):
     """The engine's stream schedules are pure re-orderings: single stream (DVD_BWD_OVERLAP=0), two-stream backward (default) and
-    two image lanes (DVD_LANES=2, opt-in) give the same depth map bit for bit and the same parameter gradients up to the order
-    of the fp32 atomics in the weight-gradient reductions."""
+    two image lanes (DVD_LANES=2, opt-in) give the same depth map and the same parameter gradients up to fp32 summation order
+    (atomics in the weight-gradient reductions, stream-K splits)."""
     net = _nets().cuda()
     x = torch.rand(4, 3, 64, 96, device='cuda')
     w = torch.rand(4, 1, 64, 96, device='cuda')
@@ -95,7 +95,8 @@ def test_stream_schedules_agree(monkeypatch):
     d0, g0 = run({'DVD_BWD_OVERLAP': '0'})
     for env in ({}, {'DVD_LANES': '2'}):
         d1, g1 = run(env)
-        assert torch.equal(d0, d1), env
+        # (identical per-element K order except where the stream-K split of a layer differs with the tile count of a lane)
+        assert float((d0 - d1).abs().max() / d0.abs().max()) < 1e-6, env
         num = sum(float(((g1[k].double() - g0[k].double()) ** 2).sum()) for k in g0)
         den = sum(float((g0[k].double() ** 2).sum()) for k in g0)
         assert (num / den) ** 0.5 < 1e-5, (env, (num / den) ** 0.5)
