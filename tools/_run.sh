@@ -1,7 +1,2 @@
 set -x
-timeout 500 python -m pytest tests/test_depth_engine_gpu.py tests/test_step_gpu.py tests/test_step_benchconfig_gpu.py tests/test_reproject_gpu.py tests/test_eval_path_gpu.py tests/test_checkpoint_compat_gpu.py tests/test_conv2d_gpu.py -x -q 2>&1 | tail -4
-timeout 200 python bench.py --pairs 1 --steps 30 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_lanes_B1.log 2>&1; tail -c 250 gpurun_out/r3_bench_lanes_B1.log
-DVD_LANES=1 timeout 200 python bench.py --pairs 1 --steps 30 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_nolanes_B1.log 2>&1; tail -c 250 gpurun_out/r3_bench_nolanes_B1.log
-timeout 200 python bench.py --pairs 2 --steps 20 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_lanes_B2.log 2>&1; tail -c 250 gpurun_out/r3_bench_lanes_B2.log
-DVD_LANES=1 timeout 200 python bench.py --pairs 2 --steps 20 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_nolanes_B2.log 2>&1; tail -c 250 gpurun_out/r3_bench_nolanes_B2.log
-timeout 100 python tools/bench_reproject.py 64 2>&1 | tail -4
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 8 --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_8gpu.log 2>gpurun_out/r3_bench_8gpu.err; echo "rc=$?"; tail -c 500 gpurun_out/r3_bench_8gpu.log; tail -3 gpurun_out/r3_bench_8gpu.err
