@@ -82,6 +82,7 @@ SIGNATURES = {
     'dvd_conv2d_nhwc': [ctypes.POINTER(ConvDesc)] + [_P] * 11 + [_P],
     'dvd_conv2d_nhwc_ws': [ctypes.POINTER(ConvDesc)] + [_P] * 11 + [_P, ctypes.c_size_t, _P],
     'dvd_conv2d_workspace_bytes': [],
+    'dvd_conv2d_streamk_bounds': [_I, _I, _I, ctypes.POINTER(ctypes.c_long)],
     'dvd_conv2d_pack': [_P, ctypes.c_long, ctypes.c_long, ctypes.c_long, ctypes.c_long, _P, _P, _I, _I, _I, _I, _I, _P, _P, _F, _P],
     'dvd_conv2d_pack_blocks': [_I, _I, _I, _I, _I],
     'dvd_conv2d_pack_batch': [_P, _I, ctypes.c_long, _I, _P],

@@ -83,7 +83,7 @@ struct ConvParams {
 struct SegIter {
   long u, u1;
   int tile, ntiles, step, ksteps, sk;
-  __device__ static long bound(long c, long n_clusters, long total, int ksteps) {
+  __host__ __device__ static long bound(long c, long n_clusters, long total, int ksteps) {
     if (c >= n_clusters) return total;
     long u = c * total / n_clusters;
     const int r = (int)(u % ksteps);
@@ -1191,6 +1191,14 @@ int max_clusters(K kernel, int threads, size_t smem_bytes, int csize) {
 }  // namespace dvd
 
 using namespace dvd;
+
+/* first (tile-major) K-step of every cluster's range under the stream-K schedule: out[0..n_clusters], out[n_clusters] = total
+ * (host restatement of the kernel's own rule, for tests of the schedule's invariants) */
+extern "C" int dvd_conv2d_streamk_bounds(int ntiles, int ksteps, int n_clusters, long* out) {
+  DVD_ARG_CHECK(out && ntiles >= 1 && ksteps >= 1 && n_clusters >= 1 && (long)ntiles * ksteps >= n_clusters, "bad schedule shape");
+  for (int c = 0; c <= n_clusters; ++c) out[c] = SegIter::bound(c, n_clusters, (long)ntiles * ksteps, ksteps);
+  return 0;
+}
 
 extern "C" size_t dvd_conv2d_workspace_bytes(void) {
   // one partial tile [128][256] fp32 and one flag per resident CTA

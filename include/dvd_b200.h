@@ -232,6 +232,8 @@ int dvd_conv2d_nhwc(const dvd_conv_desc* desc, const float* x, const float* w_im
  * dvd_conv2d_workspace_bytes() bytes of device memory, 16-byte aligned, ZEROED ONCE by the caller and then left to the library;
  * launches that share a workspace must be ordered on one stream. NULL = whole tiles only (dvd_conv2d_nhwc).                  */
 size_t dvd_conv2d_workspace_bytes(void);
+/* host restatement of the stream-K partition (no GPU needed): out[c] = first tile-major K-step of cluster c, out[n_clusters] = ntiles * ksteps */
+int dvd_conv2d_streamk_bounds(int ntiles, int ksteps, int n_clusters, long* out);
 int dvd_conv2d_nhwc_ws(const dvd_conv_desc* desc, const float* x, const float* w_img, const float* bias, const float* bn_gamma,
                        const float* bn_beta, const float* bn_mean, const float* bn_var, const float* res, const float* res2,
                        const float* mask, float* y, void* workspace, size_t workspace_bytes, void* stream);
