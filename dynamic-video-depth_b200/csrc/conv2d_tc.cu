@@ -1024,6 +1024,13 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
       sc = __ldg(P.gamma + m) * rstd;
     }
     float dot = 0.f;
+    // (first block of the gamma-gradient weights: in flight while the last MMAs run)
+    const bool wvec = !P.cpg && wrow != nullptr && P.s_n == 1 && ((reinterpret_cast<uintptr_t>(wrow + n0) & 15) == 0);
+    float4 wnext[4];
+    if (wvec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wnext[j] = __ldg(reinterpret_cast<const float4*>(wrow + n0) + j);
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (P.cpg) {
@@ -1047,11 +1054,30 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
         }
       }
     } else {
+      // the weights of the gamma-gradient dot product are loaded one block AHEAD (this loop runs after the last MMA, nothing hides
+      // its latencies): contiguous, 16-byte aligned rows (channels-last parameter buffers) as four 128-bit loads per block
       for (int c0 = 0; c0 < P.NT; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(d + c0, r);
+        float4 wcur[4];
+        if (wvec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) wcur[j] = wnext[j];
+          if (c0 + 16 < P.NT) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wnext[j] = __ldg(reinterpret_cast<const float4*>(wrow + n0 + c0 + 16) + j);
+          }
+        }
         tmem_ld_wait();
-        if (wrow) {
+        if (wvec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dot = fmaf(__uint_as_float(r[4 * j]), wcur[j].x, dot);
+            dot = fmaf(__uint_as_float(r[4 * j + 1]), wcur[j].y, dot);
+            dot = fmaf(__uint_as_float(r[4 * j + 2]), wcur[j].z, dot);
+            dot = fmaf(__uint_as_float(r[4 * j + 3]), wcur[j].w, dot);
+          }
+        } else if (wrow) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) dot = fmaf(__uint_as_float(r[j]), __ldg(wrow + (long)(n0 + c0 + j) * P.s_n), dot);
         }

@@ -1,2 +1,3 @@
 set -x
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 8 --steps 10 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_8gpu.log 2>gpurun_out/r3_bench_8gpu.err; echo "rc=$?"; tail -c 500 gpurun_out/r3_bench_8gpu.log; tail -3 gpurun_out/r3_bench_8gpu.err
+timeout 300 python -m pytest tests/test_conv2d_gpu.py tests/test_depth_engine_gpu.py -x -q 2>&1 | tail -3
+timeout 200 python bench.py --steps 20 --no-extras --no-cpu-baseline > gpurun_out/r3_bench_wgpre.log 2>&1; tail -c 200 gpurun_out/r3_bench_wgpre.log
