@@ -242,20 +242,24 @@ class MidasEngine:
         self._fork(lanes)
         # the lanes advance stage by stage (host order = lane 0, lane 1, ... within a stage): a block of parameter gradients is
         # final - and handed to the gradient exchange - when every lane has passed it
+        nm, ns = (_NORM_MEAN, _NORM_STD) if self.normalize else (None, None)
         stem = []
         for stage in ('decoder+layer4', 'layer3', 'pre-stem'):
             for ln, gen in zip(lanes, gens):
                 with self._in_lane(ln):
                     out = next(gen)
                     assert out[0] == stage
-                    self._side_join()
                     if stage == 'pre-stem':
-                        stem.append(out[1])
+                        if len(lanes) == 1:      # (while the last weight gradients are still running on the side stream)
+                            co.stem_wgrad(*out[1], self.stem_conv, self.stem_bn, nm, ns)
+                        else:
+                            stem.append(out[1])
+                    self._side_join()
             self._join(lanes)
             if stage != 'pre-stem' and self.grad_hook is not None:
                 self.grad_hook(stage)
-        # the stem's weight-gradient finalisation is a plain read-modify-write of the 3 -> 64 filter: one lane after the other
-        nm, ns = (_NORM_MEAN, _NORM_STD) if self.normalize else (None, None)
+        # several lanes: the stem's weight-gradient finalisation is a plain read-modify-write of the 3 -> 64 filter, so one lane
+        # after the other on the main stream
         for xs, g_a0, a0 in stem:
             co.stem_wgrad(xs, g_a0, a0, self.stem_conv, self.stem_bn, nm, ns)
         if self.grad_hook is not None:
