@@ -52,6 +52,7 @@ _L = ctypes.c_longlong
 # name -> argtypes; restype is int unless listed in _RESTYPES
 SIGNATURES = {
     'dvd_version': [],
+    'dvd_struct_size': [_I],
     'dvd_last_error': [],
     'dvd_reproject_partials_size': [_I, _I, _I],
     'dvd_unproject_fwd': [_P, _P, _P, _I, _I, _I, _I, _P],
@@ -100,7 +101,7 @@ SIGNATURES = {
     'dvd_head_fwd': [_P, _P, _P, _P, ctypes.c_long, _P],
     'dvd_head_bwd': [_P, _P, _P, _P, _P, _P, _P, ctypes.c_long, _I, _I, _P],
 }
-_RESTYPES = {'dvd_last_error': ctypes.c_char_p, 'dvd_conv2d_workspace_bytes': ctypes.c_size_t, 'dvd_conv2d_pack_blocks': ctypes.c_long, 'dvd_mlp_packed_weights_bytes': ctypes.c_size_t,
+_RESTYPES = {'dvd_last_error': ctypes.c_char_p, 'dvd_struct_size': ctypes.c_long, 'dvd_conv2d_workspace_bytes': ctypes.c_size_t, 'dvd_conv2d_pack_blocks': ctypes.c_long, 'dvd_mlp_packed_weights_bytes': ctypes.c_size_t,
              'dvd_mlp_save_bytes_per_eval': ctypes.c_size_t, 'dvd_mlp_dy_bytes': ctypes.c_size_t}
 
 _lib = None

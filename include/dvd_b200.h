@@ -45,6 +45,8 @@ enum { DVD_S_FLOW = 0, DVD_S_DISP = 1, DVD_S_SF = 2, DVD_S_LOSS = 3, DVD_S_MASKS
 
 const char* dvd_last_error(void);
 int dvd_version(void);
+/* sizeof of the structs passed by pointer: 0 dvd_loss_cfg, 1 dvd_mlp_cfg, 2 dvd_conv_desc, 3 dvd_pack_item (-1 otherwise) */
+long dvd_struct_size(int which);
 /* number of fp32 partial-sum slots dvd_reproject_loss_fwd needs in `partials` for a given shape */
 int dvd_reproject_partials_size(int B, int H, int W);
 

@@ -41,3 +41,13 @@ def test_ops_reject_cpu_tensors():
     from dvd_b200 import ops
     with pytest.raises(ValueError):
         ops.unproject_fwd(torch.zeros(1, 1, 8, 8), torch.zeros(1, 48), 1)
+
+
+def test_ctypes_struct_layouts_match_the_library():
+    """the four structs that cross the C ABI by pointer: the ctypes mirrors of dvd_b200/_lib.py have the sizes the compiled
+    library reports for the C definitions of include/dvd_b200.h"""
+    from dvd_b200 import _lib
+    lib = _lib.load()
+    for which, cls in enumerate((_lib.LossCfg, _lib.MlpCfg, _lib.ConvDesc, _lib.PackItem)):
+        assert lib.dvd_struct_size(which) == ctypes.sizeof(cls), (cls.__name__, lib.dvd_struct_size(which), ctypes.sizeof(cls))
+    assert lib.dvd_struct_size(99) == -1
