@@ -99,7 +99,9 @@ _WS_LANE = 0
 
 def set_workspace_lane(lane):
     """Convolutions that may run CONCURRENTLY (the lanes of depth_engine.MidasEngine: one stream each) must not share an exchange
-    area; launches of one lane are stream-ordered. Returns the previous lane."""
+    area; launches of one lane are stream-ordered. lane < 0: no exchange area, i.e. no stream-K schedule - used while SEVERAL
+    lanes are active: a stream-K launch spins in its finishing CTAs until the CTAs that hold the rest of their tiles have run, which
+    is only deadlock-free when no other spinning launch can occupy the SMs those CTAs are waiting for. Returns the previous lane."""
     global _WS_LANE
     prev, _WS_LANE = _WS_LANE, int(lane)
     return prev
@@ -110,6 +112,8 @@ def conv_workspace(device):
     lane are issued on one stream at a time (the current stream, or the capture stream of the step graph); a caller that runs
     convolutions concurrently on several streams outside the engine's lanes must set DVD_CONV_STREAMK=0. Never allocated during a
     graph capture (the eager warm-up steps before a capture have the same lanes)."""
+    if _WS_LANE < 0:
+        return None
     idx = (device.index if device.index is not None else torch.cuda.current_device(), _WS_LANE)
     ws = _WORKSPACE.get(idx)
     if ws is None:

@@ -61,7 +61,7 @@ class MidasEngine:
         self._all += [c for r in self.rcu_a[:3] + self.rcu_b for c in (r.c1, r.c2)] + [self.oc0, self.oc2]
         self.saved = None
         self._table = None
-        self._lane, self._lane_pool, self._lanes = None, {}, None
+        self._lane, self._lane_pool, self._lanes, self._n_active_lanes = None, {}, None, 1
         # called as grad_hook(stage) at the points of backward() where a contiguous block of parameter gradients is final:
         # 'decoder+layer4', 'layer3', 'rest' - the data-parallel path all-reduces that block while the backward goes on
         self.grad_hook = None
@@ -101,7 +101,8 @@ class MidasEngine:
             def __enter__(self_):
                 self_.prev = eng._lane
                 eng._lane = lane
-                self_.prev_ws = co.set_workspace_lane(lane.index)
+                # one lane: its own exchange area (stream-K allowed); several concurrent lanes: none (see set_workspace_lane)
+                self_.prev_ws = co.set_workspace_lane(lane.index if eng._n_active_lanes == 1 else -1)
                 self_.sc = torch.cuda.stream(lane.stream) if lane.stream is not None else None
                 if self_.sc is not None:
                     self_.sc.__enter__()
@@ -168,6 +169,7 @@ class MidasEngine:
         self.pack(need_bwd=train)
         x = x.contiguous()
         lanes = self._lanes_for(x.shape[0])
+        self._n_active_lanes = len(lanes)
         if len(lanes) == 1:
             with self._in_lane(lanes[0]):
                 depth, lanes[0].saved = self._forward_one(x, train)
@@ -233,6 +235,7 @@ class MidasEngine:
         if self.saved is None or lanes is None:
             raise RuntimeError('MidasEngine.backward without a training forward')
         self.saved, self._lanes = None, None
+        self._n_active_lanes = len(lanes)
         self._ensure_grads()
         g_depth = g_depth.contiguous()
         per = g_depth.shape[0] // len(lanes)

@@ -93,10 +93,13 @@ def test_stream_schedules_agree(monkeypatch):
         return d.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters()}
 
     d0, g0 = run({'DVD_BWD_OVERLAP': '0'})
-    for env in ({}, {'DVD_LANES': '2'}):
+    # tolerances: the two-stream backward changes nothing but the order of fp32 atomics; image lanes also run the few-tile layers
+    # without the stream-K schedule (another K summation order in four 18 432-term layers, carried through the decoder)
+    for env, tol_d, tol_g in (({}, 1e-6, 1e-5), ({'DVD_LANES': '2'}, 1e-3, 1e-2)):
         d1, g1 = run(env)
-        # (identical per-element K order except where the stream-K split of a layer differs with the tile count of a lane)
-        assert float((d0 - d1).abs().max() / d0.abs().max()) < 1e-6, env
+        ed = float((d0 - d1).abs().max() / d0.abs().max())
         num = sum(float(((g1[k].double() - g0[k].double()) ** 2).sum()) for k in g0)
         den = sum(float((g0[k].double() ** 2).sum()) for k in g0)
-        assert (num / den) ** 0.5 < 1e-5, (env, (num / den) ** 0.5)
+        print('schedule', env, 'depth', ed, 'grad L2', (num / den) ** 0.5)
+        assert ed < tol_d, (env, ed)
+        assert (num / den) ** 0.5 < tol_g, (env, (num / den) ** 0.5)
